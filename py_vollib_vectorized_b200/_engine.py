@@ -1,0 +1,300 @@
+"""ctypes binding of libpvv.so — the ONLY compute path of this package.
+
+There is no CPU fallback: if the shared library is missing the import fails, and if no CUDA device
+is present every call raises.  PyTorch is used for device memory, streams and pinned host memory
+only (plumbing); the arithmetic lives in csrc/*.cu behind the C ABI declared in include/pvv.h.
+
+Two families of calls:
+  *  host path   (`price`, `greeks`, `iv`, `iv_greeks`): numpy arrays (pageable or pinned) in, numpy
+     arrays out; the library runs its chunked H2D -> kernel -> D2H pipeline (pvv_*_host).
+  *  device path (`price_dev`, ...): torch CUDA tensors in/out, asynchronous on the current torch
+     stream (pvv_*_dev).
+Columns are (array, stride) pairs: stride 0 marks a broadcast scalar that is never materialised.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpvv.so")
+
+MODELS = {"black": 0, "black_scholes": 1, "black_scholes_merton": 2}
+
+ST_BELOW_INTRINSIC, ST_ABOVE_MAXIMUM, ST_ZERO_DIVISION, ST_DEFLATER_ZERO = 1, 2, 4, 8
+
+_INT64_MAX = np.iinfo(np.int64).max
+
+
+class PvvError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA engine has not been built "
+            "(run `python py_vollib_vectorized_b200/build.py`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.pvv_version.restype = i32
+    lib.pvv_error_string.restype = ctypes.c_char_p
+    lib.pvv_error_string.argtypes = [i32]
+    lib.pvv_launch_count.restype = i64
+    lib.pvv_ctx_create.argtypes = [i32, i64, i32, ctypes.POINTER(vp)]
+    lib.pvv_ctx_destroy.argtypes = [vp]
+    lib.pvv_ctx_destroy.restype = None
+    # (model, n, flag, 6 cols, stride, outputs..., first_zde[, stream])
+    lib.pvv_price_dev.argtypes = [i32, i64] + [vp] * 7 + [vp, vp, vp, vp]
+    lib.pvv_greeks_dev.argtypes = [i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp, vp]
+    lib.pvv_iv_dev.argtypes = [i32, i64] + [vp] * 7 + [vp, i32, vp, vp, vp, vp]
+    lib.pvv_iv_greeks_dev.argtypes = [i32, i64] + [vp] * 7 + [vp, i32, vp, vp] + [vp] * 5 + [vp, vp]
+    lib.pvv_price_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, vp, vp]
+    lib.pvv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp]
+    lib.pvv_iv_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp, vp]
+    lib.pvv_iv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp] + [vp] * 5 + [vp]
+    lib.pvv_unary_dev.argtypes = [i32, i64, vp, vp, vp]
+    lib.pvv_fp64_probe.argtypes = [i64, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
+    return lib
+
+
+_lib = _load()
+
+
+def lib():
+    return _lib
+
+
+def launch_count():
+    return int(_lib.pvv_launch_count())
+
+
+def _check(code):
+    if code != 0:
+        raise PvvError(f"libpvv call failed ({code}): {_lib.pvv_error_string(code).decode()}")
+
+
+# ------------------------------------------------------------------------------------------------
+# host path
+# ------------------------------------------------------------------------------------------------
+class _Ctx:
+    """One pvv_ctx (streams + device slots) per (device, chunk) — created on first use."""
+
+    def __init__(self, device, chunk, nstreams):
+        self.handle = ctypes.c_void_p()
+        _check(_lib.pvv_ctx_create(device, chunk, nstreams, ctypes.byref(self.handle)))
+        self.lock = threading.Lock()
+
+    def close(self):
+        if self.handle:
+            _lib.pvv_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_ctxs = {}
+_ctx_lock = threading.Lock()
+
+
+def get_ctx(device=None, chunk=0, nstreams=0):
+    if device is None:
+        device = int(os.environ.get("PVV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    key = (device, chunk, nstreams)
+    with _ctx_lock:
+        c = _ctxs.get(key)
+        if c is None:
+            c = _ctxs[key] = _Ctx(device, chunk, nstreams)
+        return c
+
+
+def _hp(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _hcol(col):
+    """(array|None, stride) -> contiguous float64 host array (kept alive by the caller) and stride."""
+    if col is None:
+        return None, 0
+    a, s = col
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, int(s)
+
+
+def _hflag(col):
+    a, s = col
+    return np.ascontiguousarray(a, dtype=np.int8), int(s)
+
+
+def _raise_zde(first):
+    if first >= 0:
+        # numba's error model raises for the whole call
+        raise ZeroDivisionError("division by zero")
+
+
+def price(model, n, flag, S, K, t, r, q, sigma, *, ctx=None, out=None, raise_zde=True):
+    """Host path of K1.  Columns are (array, stride) pairs; returns a float64 array of n prices."""
+    ctx = ctx or get_ctx()
+    f, sf = _hflag(flag)
+    cols = [_hcol(c) for c in (S, K, t, r, q, sigma)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    out = np.empty(n, dtype=np.float64) if out is None else out
+    first = ctypes.c_int64(-1)
+    with ctx.lock:
+        _check(_lib.pvv_price_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), _hp(out),
+                                   ctypes.byref(first)))
+    if raise_zde:
+        _raise_zde(first.value)
+    return out
+
+
+GREEK_NAMES = ("delta", "gamma", "theta", "rho", "vega")
+
+
+def greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price=False, ctx=None, outs=None, raise_zde=True):
+    """Host path of K2.  Returns dict name -> float64 array for the requested outputs."""
+    ctx = ctx or get_ctx()
+    f, sf = _hflag(flag)
+    cols = [_hcol(c) for c in (S, K, t, r, q, sigma)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    names = (("price",) if with_price else ()) + tuple(want)
+    outs = outs or {k: np.empty(n, dtype=np.float64) for k in names}
+    first = ctypes.c_int64(-1)
+    ptrs = [_hp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
+    with ctx.lock:
+        _check(_lib.pvv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), *ptrs,
+                                    ctypes.byref(first)))
+    if raise_zde:
+        _raise_zde(first.value)
+    return outs
+
+
+def iv(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, ctx=None, out=None, status=None):
+    """Host path of K3.  Returns (iv, status, first_zero_division_index)."""
+    ctx = ctx or get_ctx()
+    f, sf = _hflag(flag)
+    cols = [_hcol(c) for c in (price_col, S, K, t, r, q)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    out = np.empty(n, dtype=np.float64) if out is None else out
+    status = np.empty(n, dtype=np.uint8) if status is None else status
+    first = ctypes.c_int64(-1)
+    with ctx.lock:
+        _check(_lib.pvv_iv_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), int(bool(mask_errors)),
+                                _hp(out), _hp(status), ctypes.byref(first)))
+    return out, status, first.value
+
+
+def iv_greeks(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, want=GREEK_NAMES, ctx=None, outs=None, status=None):
+    """Host path of K4.  Returns (dict(iv, greeks...), status, first_zero_division_index)."""
+    ctx = ctx or get_ctx()
+    f, sf = _hflag(flag)
+    cols = [_hcol(c) for c in (price_col, S, K, t, r, q)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    outs = outs or {k: np.empty(n, dtype=np.float64) for k in ("iv",) + tuple(want)}
+    status = np.empty(n, dtype=np.uint8) if status is None else status
+    first = ctypes.c_int64(-1)
+    ptrs = [_hp(outs.get(k)) for k in GREEK_NAMES]
+    with ctx.lock:
+        _check(_lib.pvv_iv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride),
+                                       int(bool(mask_errors)), _hp(outs["iv"]), _hp(status), *ptrs, ctypes.byref(first)))
+    return outs, status, first.value
+
+
+# ------------------------------------------------------------------------------------------------
+# device path (torch CUDA tensors; asynchronous on the current torch stream)
+# ------------------------------------------------------------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+def _dp(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _dcol(t, n, dtype):
+    torch = _torch()
+    if t is None:
+        return None, 0
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError("device columns must be contiguous CUDA tensors of dtype %s" % dtype)
+    if t.numel() == n:
+        return t, 1
+    if t.numel() == 1:
+        return t, 0
+    raise ValueError("device column has %d elements, expected %d or 1" % (t.numel(), n))
+
+
+def _stream_ptr():
+    torch = _torch()
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def new_zde_word(device):
+    torch = _torch()
+    return torch.full((1,), _INT64_MAX, dtype=torch.int64, device=device)
+
+
+def price_dev(model, n, flag, S, K, t, r, q, sigma, out, first_zde=None):
+    torch = _torch()
+    f, sf = _dcol(flag, n, torch.int8)
+    cols = [_dcol(c, n, torch.float64) for c in (S, K, t, r, q, sigma)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    _check(_lib.pvv_price_dev(MODELS[model], n, _dp(f), *[_dp(c[0]) for c in cols], _hp(stride), _dp(out), _dp(first_zde), _stream_ptr()))
+    return out
+
+
+def greeks_dev(model, n, flag, S, K, t, r, q, sigma, outs, first_zde=None):
+    """outs: dict with any of price/delta/gamma/theta/rho/vega -> preallocated CUDA float64 tensors."""
+    torch = _torch()
+    f, sf = _dcol(flag, n, torch.int8)
+    cols = [_dcol(c, n, torch.float64) for c in (S, K, t, r, q, sigma)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    ptrs = [_dp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
+    _check(_lib.pvv_greeks_dev(MODELS[model], n, _dp(f), *[_dp(c[0]) for c in cols], _hp(stride), *ptrs, _dp(first_zde), _stream_ptr()))
+    return outs
+
+
+def iv_dev(model, n, flag, price_col, S, K, t, r, q, out, status, mask_errors=True, first_zde=None):
+    torch = _torch()
+    f, sf = _dcol(flag, n, torch.int8)
+    cols = [_dcol(c, n, torch.float64) for c in (price_col, S, K, t, r, q)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    _check(_lib.pvv_iv_dev(MODELS[model], n, _dp(f), *[_dp(c[0]) for c in cols], _hp(stride), int(bool(mask_errors)), _dp(out), _dp(status),
+                           _dp(first_zde), _stream_ptr()))
+    return out, status
+
+
+def iv_greeks_dev(model, n, flag, price_col, S, K, t, r, q, iv_out, status, outs, mask_errors=True, first_zde=None):
+    torch = _torch()
+    f, sf = _dcol(flag, n, torch.int8)
+    cols = [_dcol(c, n, torch.float64) for c in (price_col, S, K, t, r, q)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    ptrs = [_dp(outs.get(k)) for k in GREEK_NAMES]
+    _check(_lib.pvv_iv_greeks_dev(MODELS[model], n, _dp(f), *[_dp(c[0]) for c in cols], _hp(stride), int(bool(mask_errors)), _dp(iv_out),
+                                  _dp(status), *ptrs, _dp(first_zde), _stream_ptr()))
+    return iv_out, status, outs
+
+
+UNARY = {"exp": 0, "log": 1, "erfcx": 2, "erfc": 3, "norm_cdf": 4, "inverse_norm_cdf": 5}
+
+
+def unary_dev(which, x):
+    """Diagnostic: evaluates one of the device scalar functions over a CUDA float64 tensor."""
+    torch = _torch()
+    y = torch.empty_like(x)
+    _check(_lib.pvv_unary_dev(UNARY[which], x.numel(), _dp(x), _dp(y), _stream_ptr()))
+    return y
+
+
+def fp64_probe(threads=148 * 2048, iters=4096, use_fma=False):
+    """Measured FP64 issue rate in DP instructions/s (dependent DMUL+DADD or DFMA chains)."""
+    ms = ctypes.c_float(0)
+    _check(_lib.pvv_fp64_probe(threads, iters, int(use_fma), ctypes.byref(ms), _stream_ptr()))
+    instr = float(threads) * iters * 16
+    return instr / (ms.value * 1e-3)

@@ -1,0 +1,61 @@
+"""Builds libpvv.so (the CUDA engine + C ABI) in-tree with nvcc for sm_100a.
+
+    python py_vollib_vectorized_b200/build.py [--force] [--verbose]
+
+-fmad=false is part of the numerical contract (see csrc/pvv_math.cuh): the reference's numba loops
+never contract a*b+c, and bit-identical stencil prices are what makes the finite-difference greeks
+match.  Explicit fma() calls (glibc's exp/log) are unaffected by the flag.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpvv.so")
+SOURCES = [os.path.join(CSRC, "pvv_kernels.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "pvv_math.cuh"), os.path.join(CSRC, "glibc_tables.cuh"),
+                  os.path.join(os.path.dirname(HERE), "include", "pvv.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
+    "--shared", "-cudart", "shared",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA engine cannot be built (there is no CPU fallback)")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_extension(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    env = dict(os.environ)
+    # the image's default CC wrapper lacks some specs; the system g++ is the host compiler
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libpvv.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_extension(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

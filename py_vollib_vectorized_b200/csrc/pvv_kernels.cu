@@ -1,0 +1,593 @@
+// pvv_kernels.cu — sm_100a kernels and the C ABI (include/pvv.h) of the B200 engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false
+//        (-fmad=false is part of the numerical contract, see pvv_math.cuh)
+//
+// Data layout in HBM: structure of arrays — one int8 flag column and one float64 column per input,
+// each either dense (stride 1) or a single broadcast scalar (stride 0); one float64 column per
+// output (+ one uint8 status column for the IV kernels).  One thread per contract, consecutive
+// threads read consecutive elements: every warp-level access is a fully coalesced 256-byte line
+// pair.  The kernels are FP64-pipe bound (hundreds to thousands of DP instructions per 50-100 bytes
+// of traffic), so the launch shape is chosen for occupancy of the FP64 pipe, not for bandwidth.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <climits>
+#include <cstdio>
+#include <new>
+
+#include "../../include/pvv.h"
+#include "pvv_math.cuh"
+
+namespace {
+
+using pvv::Greeks;
+
+std::atomic<long long> g_launches{0};
+
+struct Strides {
+    int s[7];
+};
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
+    if (first_zde) atomicMin(first_zde, i);
+}
+
+// ---- K1: price --------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(kBlock) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+                                                       const double *__restrict__ K, const double *__restrict__ t,
+                                                       const double *__restrict__ r, const double *__restrict__ q,
+                                                       const double *__restrict__ sigma, Strides st, double *__restrict__ price,
+                                                       long long *first_zde, long long base) {
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const double f = (double)flag[i * st.s[0]];
+    const double rr = (MODEL == pvv::MODEL_BLACK) ? 0.0 : r[i * st.s[4]];
+    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
+    unsigned status = 0;
+    price[i] = pvv::price_model<MODEL>(f, S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], rr, sigma[i * st.s[6]], qq, status);
+    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+}
+
+// ---- K2: finite-difference greeks ---------------------------------------------------------------
+// The eight stencil points are evaluated by ONE loop body (code for a price exists once in the
+// kernel; the instruction cache matters more here than unrolling), skipping points no requested
+// output needs.  `want` bits: 1 price, 2 delta, 4 gamma, 8 theta, 16 rho, 32 vega.
+enum : unsigned { W_PRICE = 1, W_DELTA = 2, W_GAMMA = 4, W_THETA = 8, W_RHO = 16, W_VEGA = 32 };
+
+template <int MODEL>
+__device__ __forceinline__ Greeks greeks_stencil(double flag, double S, double K, double t, double r, double sigma, double q, unsigned want,
+                                                 unsigned &status) {
+    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
+    const double dS = .01;
+    const double b = BSM ? r - q : r;     // api.py:241 (host side of the reference)
+    const double qe = BSM ? r - b : 0.0;  // _numerical_greeks.py: black_scholes_merton(..., r - b)
+    const bool t0 = (t == 0.0);
+    // which stencil points are needed: 0 base, 1/2 S+-dS, 3 theta, 4/5 r+-0.01, 6/7 sigma+-0.01
+    unsigned need = 0;
+    if (want & (W_PRICE | W_GAMMA | W_THETA)) need |= 1u;
+    if (want & (W_DELTA | W_GAMMA)) need |= t0 ? 0u : 6u;
+    if (want & W_THETA) need |= 8u;
+    if (want & W_RHO) need |= 0x30u;
+    if (want & W_VEGA) need |= 0xc0u;
+    double p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) p[e] = 0.0;
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+        if (!((need >> e) & 1u)) continue;
+        double Se = S, te = t, re = r, se = sigma, qv = qe;
+        if (e == 1) Se = S + dS;
+        if (e == 2) Se = S - dS;
+        if (e == 3) te = (t <= 1. / 365.) ? 0.00001 : t - 1. / 365.;
+        if (e == 4) { re = r + 0.01; qv = BSM ? r - b + 0.01 : 0.0; }
+        if (e == 5) { re = r - 0.01; qv = BSM ? r - b - 0.01 : 0.0; }
+        if (e == 6) se = sigma + 0.01;
+        if (e == 7) se = sigma - 0.01;
+        const double v = pvv::price_model<MODEL>(flag, Se, K, te, re, se, qv, status);
+        // static indexing keeps p[] in registers
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j == e) p[j] = v;
+    }
+    Greeks g;
+    g.price = p[0];
+    if (t0) {
+        g.delta = (S == K) ? (flag > 0 ? 0.5 : -0.5) : (S > K ? (flag > 0 ? 1.0 : 0.0) : (flag > 0 ? 0.0 : -1.0));
+        g.gamma = (S == K) ? pvv::u2d(0x7ff0000000000000ull) : 0.0;
+    } else {
+        g.delta = (p[1] - p[2]) / (2 * dS);
+        g.gamma = (p[1] - 2. * p[0] + p[2]) / 0x1.a36e2eb1c432dp-14;  // dS ** 2.
+    }
+    g.theta = p[3] - p[0];
+    g.rho = (p[4] - p[5]) / 2.;
+    g.vega = (p[6] - p[7]) / 2.;
+    return g;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kBlock) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+                                                        const double *__restrict__ K, const double *__restrict__ t,
+                                                        const double *__restrict__ r, const double *__restrict__ q,
+                                                        const double *__restrict__ sigma, Strides st, double *__restrict__ price,
+                                                        double *__restrict__ delta, double *__restrict__ gamma,
+                                                        double *__restrict__ theta, double *__restrict__ rho, double *__restrict__ vega,
+                                                        long long *first_zde, long long base) {
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
+                          (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
+    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
+    unsigned status = 0;
+    const Greeks g = greeks_stencil<MODEL>((double)flag[i * st.s[0]], S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], r[i * st.s[4]],
+                                           sigma[i * st.s[6]], qq, want, status);
+    if (price) price[i] = g.price;
+    if (delta) delta[i] = g.delta;
+    if (gamma) gamma[i] = g.gamma;
+    if (theta) theta[i] = g.theta;
+    if (rho) rho[i] = g.rho;
+    if (vega) vega[i] = g.vega;
+    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+}
+
+// ---- K3: implied volatility ("Let's be rational") ------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(kBlock) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
+                                                    const double *__restrict__ S, const double *__restrict__ K,
+                                                    const double *__restrict__ t, const double *__restrict__ r,
+                                                    const double *__restrict__ q, Strides st, int mask_errors, double *__restrict__ iv,
+                                                    uint8_t *__restrict__ status_out, long long *first_zde, long long base) {
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+    unsigned status = 0;
+    iv[i] = pvv::implied_vol<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
+                                    r[i * st.s[5]], qq, mask_errors != 0, status);
+    if (status_out) status_out[i] = (uint8_t)status;
+    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+}
+
+// ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
+template <int MODEL>
+__global__ void __launch_bounds__(kBlock) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
+                                                           const double *__restrict__ S, const double *__restrict__ K,
+                                                           const double *__restrict__ t, const double *__restrict__ r,
+                                                           const double *__restrict__ q, Strides st, int mask_errors,
+                                                           double *__restrict__ iv, uint8_t *__restrict__ status_out,
+                                                           double *__restrict__ delta, double *__restrict__ gamma,
+                                                           double *__restrict__ theta, double *__restrict__ rho,
+                                                           double *__restrict__ vega, long long *first_zde, long long base) {
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const double f = (double)flag[i * st.s[0]];
+    const double Si = S[i * st.s[2]], Ki = K[i * st.s[3]], ti = t[i * st.s[4]], ri = r[i * st.s[5]];
+    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+    unsigned status = 0;
+    const double vol = pvv::implied_vol<MODEL>(f, price[i * st.s[1]], Si, Ki, ti, ri, qq, mask_errors != 0, status);
+    iv[i] = vol;
+    const unsigned want = (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) | (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
+    constexpr int GM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? pvv::MODEL_BLACK_SCHOLES_MERTON : pvv::MODEL_BLACK_SCHOLES;
+    unsigned gstatus = 0;
+    const Greeks g = greeks_stencil<GM>(f, Si, Ki, ti, ri, vol, qq, want, gstatus);
+    status |= gstatus & pvv::ST_ZERO_DIVISION;
+    if (status_out) status_out[i] = (uint8_t)status;
+    if (delta) delta[i] = g.delta;
+    if (gamma) gamma[i] = g.gamma;
+    if (theta) theta[i] = g.theta;
+    if (rho) rho[i] = g.rho;
+    if (vega) vega[i] = g.vega;
+    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------
+__global__ void unary_kernel(int which, long long n, const double *__restrict__ x, double *__restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double o;
+    switch (which) {
+        case 0: o = pvv::exp_g(v); break;
+        case 1: o = pvv::log_g(v); break;
+        case 2: o = pvv::erfcx_cody(v); break;
+        case 3: o = pvv::erfc_cody(v); break;
+        case 4: o = pvv::norm_cdf(v); break;
+        default: o = pvv::inverse_norm_cdf(v); break;
+    }
+    y[i] = o;
+}
+
+// Dependent chains of DP instructions, 8 independent chains per thread: measures the FP64 issue
+// rate the roofline of the FP64-bound kernels is quoted against (MEASURED_PEAKS.json has none).
+template <bool FMA>
+__global__ void fp64_probe_kernel(int iters, double *out) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double m = 1.0000000001, c = 1e-12;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (FMA) {
+                a[j] = __fma_rn(a[j], m, c);
+                a[j] = __fma_rn(a[j], m, c);
+            } else {
+                a[j] = __dmul_rn(a[j], m);
+                a[j] = __dadd_rn(a[j], c);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;
+}
+
+inline int grid_for(long long n) { return (int)((n + kBlock - 1) / kBlock); }
+
+inline bool fill_strides(const int64_t *stride, Strides &out) {
+    for (int i = 0; i < 7; ++i) {
+        if (stride[i] != 0 && stride[i] != 1) return false;
+        out.s[i] = (int)stride[i];
+    }
+    return true;
+}
+
+inline int launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int pvv_version(void) { return 100; }
+
+const char *pvv_error_string(int code) {
+    if (code == 0) return "success";
+    if (code == PVV_E_INVALID_ARGUMENT) return "pvv: invalid argument";
+    if (code == PVV_E_NO_DEVICE) return "pvv: no CUDA device";
+    if (code == PVV_E_OUT_OF_MEMORY) return "pvv: out of memory";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "pvv: unknown error";
+}
+
+int64_t pvv_launch_count(void) { return g_launches.load(); }
+
+static int launch_price(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
+                        const double *q, const double *sigma, const int64_t stride[7], double *price, int64_t *first_zde, long long base,
+                        void *stream) {
+    Strides st;
+    if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
+    if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long *fz = (long long *)first_zde;
+    if (model == 0) price_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    else if (model == 1) price_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    else price_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    g_launches++;
+    return launch_status();
+}
+
+static int launch_greeks(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
+                         const double *q, const double *sigma, const int64_t stride[7], double *price, double *delta, double *gamma,
+                         double *theta, double *rho, double *vega, int64_t *first_zde, long long base, void *stream) {
+    Strides st;
+    if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
+    if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long *fz = (long long *)first_zde;
+    if (model == 2) greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    else greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    g_launches++;
+    return launch_status();
+}
+
+static int launch_iv(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
+                     const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
+                     int64_t *first_zde, long long base, void *stream) {
+    Strides st;
+    if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
+    if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long *fz = (long long *)first_zde;
+    if (model == 0) iv_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    else if (model == 1) iv_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    else iv_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    g_launches++;
+    return launch_status();
+}
+
+static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K,
+                            const double *t, const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv,
+                            uint8_t *status, double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde,
+                            long long base, void *stream) {
+    Strides st;
+    if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
+    if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long *fz = (long long *)first_zde;
+    if (model == 0)
+        iv_greeks_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+    else if (model == 1)
+        iv_greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+    else
+        iv_greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+    g_launches++;
+    return launch_status();
+}
+
+int pvv_price_dev(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
+                  const double *q, const double *sigma, const int64_t stride[7], double *price, int64_t *first_zde, void *stream) {
+    return launch_price(model, n, flag, S, K, t, r, q, sigma, stride, price, first_zde, 0, stream);
+}
+int pvv_greeks_dev(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
+                   const double *q, const double *sigma, const int64_t stride[7], double *price, double *delta, double *gamma,
+                   double *theta, double *rho, double *vega, int64_t *first_zde, void *stream) {
+    return launch_greeks(model, n, flag, S, K, t, r, q, sigma, stride, price, delta, gamma, theta, rho, vega, first_zde, 0, stream);
+}
+int pvv_iv_dev(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
+               const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
+               int64_t *first_zde, void *stream) {
+    return launch_iv(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, first_zde, 0, stream);
+}
+int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
+                      const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
+                      double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream) {
+    return launch_iv_greeks(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, delta, gamma, theta, rho, vega,
+                            first_zde, 0, stream);
+}
+
+int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void *stream) {
+    if (n <= 0) return n == 0 ? 0 : PVV_E_INVALID_ARGUMENT;
+    unary_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, n, x, y);
+    g_launches++;
+    return launch_status();
+}
+
+int pvv_fp64_probe(int64_t threads, int iters, int use_fma, float *ms, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    double *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, 8);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int block = 256;
+    const int grid = (int)((threads + block - 1) / block);
+    for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+        cudaEventRecord(a, s);
+        if (use_fma) fp64_probe_kernel<true><<<grid, block, 0, s>>>(iters, out);
+        else fp64_probe_kernel<false><<<grid, block, 0, s>>>(iters, out);
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+    }
+    g_launches += 2;
+    cudaEventElapsedTime(ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    return launch_status();
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host-buffer pipeline: chunks of `chunk` contracts round-robin over `nstreams` streams; each stream
+// owns one device slot (inputs + outputs).  H2D(k+1), kernel(k) and D2H(k-1) overlap across streams
+// on the two copy engines.  Dense columns are copied chunk by chunk, broadcast scalars once.
+// With pinned (cudaHostAlloc / cudaHostRegister) user buffers every copy is a true async DMA; with
+// pageable buffers cudaMemcpyAsync falls back to the driver's staged copy (correct, slower).
+// -------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct pvv_ctx {
+    int device;
+    int nstreams;
+    long long chunk;
+    cudaStream_t stream[8];
+    char *slot[8];        // device memory of one chunk: 8 double columns in, 6 double columns out, flag, status
+    double *scalars;      // device copies of broadcast scalars: 8 doubles + 8 bytes for the flag
+    long long *first_zde; // device int64
+};
+
+namespace {
+constexpr int kInCols = 7;   // double input columns per slot (price,S,K,t,r,q,sigma — a superset of every entry point)
+constexpr int kOutCols = 6;  // double output columns per slot
+
+inline size_t slot_bytes(long long chunk) { return (size_t)chunk * (8 * (kInCols + kOutCols) + 2); }
+
+struct SlotView {
+    double *in[kInCols];
+    double *out[kOutCols];
+    int8_t *flag;
+    uint8_t *status;
+};
+inline SlotView view(const pvv_ctx *c, int i) {
+    SlotView v;
+    char *p = c->slot[i];
+    for (int k = 0; k < kInCols; ++k) { v.in[k] = (double *)p; p += 8 * c->chunk; }
+    for (int k = 0; k < kOutCols; ++k) { v.out[k] = (double *)p; p += 8 * c->chunk; }
+    v.flag = (int8_t *)p; p += c->chunk;
+    v.status = (uint8_t *)p;
+    return v;
+}
+
+#define PVV_CK(call)                      \
+    do {                                  \
+        cudaError_t e_ = (call);          \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+// Shared driver of the four host entry points.
+//   in[k]/in_stride[k]: host double columns (k < n_in), flag/flag_stride: host int8 column
+//   out[k]: host double output columns (k < n_out, NULL = not wanted), status: host uint8 (may be NULL)
+//   launch(slotview, dev_in[], dev_flag, strides, n_chunk, stream): enqueues the kernel
+template <class Launch>
+int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_stride, int n_in, const double *const *in,
+                 const long long *in_stride, int n_out, double *const *out, uint8_t *status, int64_t *first_zde, Launch launch) {
+    PVV_CK(cudaSetDevice(c->device));
+    const long long big = LLONG_MAX;
+    PVV_CK(cudaMemcpyAsync(c->first_zde, &big, 8, cudaMemcpyHostToDevice, c->stream[0]));
+    // broadcast scalars: one upload
+    double hs[8] = {0};
+    for (int k = 0; k < n_in; ++k)
+        if (in_stride[k] == 0 && in[k]) hs[k] = in[k][0];
+    PVV_CK(cudaMemcpyAsync(c->scalars, hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream[0]));
+    int8_t hf[8] = {0};
+    if (flag_stride == 0) hf[0] = flag[0];
+    PVV_CK(cudaMemcpyAsync((char *)c->scalars + 64, hf, 8, cudaMemcpyHostToDevice, c->stream[0]));
+    PVV_CK(cudaStreamSynchronize(c->stream[0]));
+    long long nchunks = (n + c->chunk - 1) / c->chunk;
+    for (long long k = 0; k < nchunks; ++k) {
+        const int si = (int)(k % c->nstreams);
+        cudaStream_t s = c->stream[si];
+        const long long off = k * c->chunk;
+        const long long m = (n - off < c->chunk) ? (n - off) : c->chunk;
+        SlotView v = view(c, si);
+        const double *dev_in[kInCols];
+        for (int j = 0; j < n_in; ++j) {
+            if (!in[j]) { dev_in[j] = nullptr; continue; }
+            if (in_stride[j] == 0) dev_in[j] = c->scalars + j;
+            else {
+                PVV_CK(cudaMemcpyAsync(v.in[j], in[j] + off, 8 * m, cudaMemcpyHostToDevice, s));
+                dev_in[j] = v.in[j];
+            }
+        }
+        const int8_t *dev_flag;
+        if (flag_stride == 0) dev_flag = (const int8_t *)((char *)c->scalars + 64);
+        else {
+            PVV_CK(cudaMemcpyAsync(v.flag, flag + off, m, cudaMemcpyHostToDevice, s));
+            dev_flag = v.flag;
+        }
+        int rc = launch(v, dev_in, dev_flag, m, off, s);
+        if (rc != 0) return rc;
+        for (int j = 0; j < n_out; ++j)
+            if (out[j]) PVV_CK(cudaMemcpyAsync(out[j] + off, v.out[j], 8 * m, cudaMemcpyDeviceToHost, s));
+        if (status) PVV_CK(cudaMemcpyAsync(status + off, v.status, m, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < c->nstreams; ++i) PVV_CK(cudaStreamSynchronize(c->stream[i]));
+    long long fz = big;
+    PVV_CK(cudaMemcpy(&fz, c->first_zde, 8, cudaMemcpyDeviceToHost));
+    if (first_zde) *first_zde = (fz == big) ? -1 : fz;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pvv_ctx_create(int device, int64_t chunk_contracts, int n_streams, pvv_ctx **out) {
+    if (!out) return PVV_E_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return PVV_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return PVV_E_INVALID_ARGUMENT;
+    pvv_ctx *c = new (std::nothrow) pvv_ctx();
+    if (!c) return PVV_E_OUT_OF_MEMORY;
+    c->device = device;
+    c->chunk = chunk_contracts > 0 ? chunk_contracts : (4ll << 20);
+    c->nstreams = n_streams > 0 ? (n_streams > 8 ? 8 : n_streams) : 3;
+    cudaError_t e = cudaSetDevice(device);
+    for (int i = 0; i < c->nstreams && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&c->slot[i], slot_bytes(c->chunk));
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&c->scalars, 128);
+    if (e == cudaSuccess) e = cudaMalloc(&c->first_zde, 8);
+    if (e != cudaSuccess) {
+        pvv_ctx_destroy(c);
+        return (int)e;
+    }
+    *out = c;
+    return 0;
+}
+
+void pvv_ctx_destroy(pvv_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < c->nstreams; ++i) {
+        if (c->stream[i]) cudaStreamSynchronize(c->stream[i]);
+        if (c->slot[i]) cudaFree(c->slot[i]);
+        if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    }
+    if (c->scalars) cudaFree(c->scalars);
+    if (c->first_zde) cudaFree(c->first_zde);
+    delete c;
+}
+
+int pvv_price_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t,
+                   const double *r, const double *q, const double *sigma, const int64_t stride[7], double *price, int64_t *first_zde) {
+    if (!ctx || n < 0 || model < 0 || model > 2 || !price || (model == 2 && !q)) return PVV_E_INVALID_ARGUMENT;
+    if (first_zde) *first_zde = -1;
+    if (n == 0) return 0;
+    const double *in[7] = {nullptr, S, K, t, (model == 0) ? nullptr : r, (model == 2) ? q : nullptr, sigma};
+    const long long ist[7] = {0, stride[1], stride[2], stride[3], stride[4], stride[5], stride[6]};
+    double *out[1] = {price};
+    return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 1, out, nullptr, first_zde,
+                        [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long off, cudaStream_t s) {
+                            return launch_price(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, v.out[0],
+                                                (int64_t *)ctx->first_zde, off, s);
+                        });
+}
+
+int pvv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t,
+                    const double *r, const double *q, const double *sigma, const int64_t stride[7], double *price, double *delta,
+                    double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde) {
+    if (!ctx || n < 0 || model < 0 || model > 2 || (model == 2 && !q)) return PVV_E_INVALID_ARGUMENT;
+    if (first_zde) *first_zde = -1;
+    if (n == 0) return 0;
+    const double *in[7] = {nullptr, S, K, t, r, (model == 2) ? q : nullptr, sigma};
+    const long long ist[7] = {0, stride[1], stride[2], stride[3], stride[4], stride[5], stride[6]};
+    double *out[6] = {price, delta, gamma, theta, rho, vega};
+    return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 6, out, nullptr, first_zde,
+                        [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long off, cudaStream_t s) {
+                            return launch_greeks(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, price ? v.out[0] : nullptr,
+                                                 delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr, theta ? v.out[3] : nullptr,
+                                                 rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr, (int64_t *)ctx->first_zde, off, s);
+                        });
+}
+
+int pvv_iv_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K,
+                const double *t, const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv,
+                uint8_t *status, int64_t *first_zde) {
+    if (!ctx || n < 0 || model < 0 || model > 2 || !iv || (model == 2 && !q)) return PVV_E_INVALID_ARGUMENT;
+    if (first_zde) *first_zde = -1;
+    if (n == 0) return 0;
+    const double *in[7] = {nullptr, price, S, K, t, r, (model == 2) ? q : nullptr};
+    const long long ist[7] = {0, stride[1], stride[2], stride[3], stride[4], stride[5], stride[6]};
+    double *out[1] = {iv};
+    return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 1, out, status, first_zde,
+                        [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long off, cudaStream_t s) {
+                            return launch_iv(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, mask_errors, v.out[0], v.status,
+                                             (int64_t *)ctx->first_zde, off, s);
+                        });
+}
+
+int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K,
+                       const double *t, const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv,
+                       uint8_t *status, double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde) {
+    if (!ctx || n < 0 || model < 0 || model > 2 || !iv || (model == 2 && !q)) return PVV_E_INVALID_ARGUMENT;
+    if (first_zde) *first_zde = -1;
+    if (n == 0) return 0;
+    const double *in[7] = {nullptr, price, S, K, t, r, (model == 2) ? q : nullptr};
+    const long long ist[7] = {0, stride[1], stride[2], stride[3], stride[4], stride[5], stride[6]};
+    double *out[6] = {iv, delta, gamma, theta, rho, vega};
+    return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 6, out, status, first_zde,
+                        [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long off, cudaStream_t s) {
+                            return launch_iv_greeks(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, mask_errors, v.out[0],
+                                                    v.status, delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr,
+                                                    theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
+                                                    (int64_t *)ctx->first_zde, off, s);
+                        });
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""GPU tier: the CUDA engine (through the C ABI, host-buffer and device-pointer entry points) against
+the CPU oracle and the committed golden vectors generated from the reference.
+
+Tolerances (BASELINE.json north_star): prices and greeks 1e-12 relative, IV 1e-10 absolute, NaN /
+error positions identical.  Prices and greeks are in fact required to be BIT-IDENTICAL here (that is
+what makes the finite-difference greeks meet 1e-12); IV is bit-identical except where the lowest
+solver branch goes through pow(x, 1/3), the one libm call not reproduced bit for bit.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from tests.util import assert_bit_equal, bit_equal
+
+pytestmark = pytest.mark.gpu
+
+GREEKS = ("delta", "gamma", "theta", "rho", "vega")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from py_vollib_vectorized_b200 import _engine
+    return _engine
+
+
+def col(a):
+    a = np.ascontiguousarray(a)
+    return (a, 1)
+
+
+def run_price(eng, model, g):
+    n = g["S"].size
+    return eng.price(model, n, col(g["flag"]), col(g["S"]), col(g["K"]), col(g["t"]), col(g["r"]),
+                     col(g["q"]) if model == "black_scholes_merton" else None, col(g["sigma"]))
+
+
+def run_greeks(eng, model, g, **kw):
+    n = g["S"].size
+    return eng.greeks(model, n, col(g["flag"]), col(g["S"]), col(g["K"]), col(g["t"]), col(g["r"]),
+                      col(g["q"]) if model == "black_scholes_merton" else None, col(g["sigma"]), **kw)
+
+
+def run_iv(eng, model, g, price, mask=True):
+    n = g["S"].size
+    return eng.iv(model, n, col(g["flag"]), col(price), col(g["S"]), col(g["K"]), col(g["t"]), col(g["r"]),
+                  col(g["q"]) if model == "black_scholes_merton" else None, mask_errors=mask)
+
+
+def test_device_exp_log_are_the_host_libm(eng, oracle):
+    """exp_g / log_g must return glibc's bits (the reference's numba loops call the host libm)."""
+    import torch
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(-745, 709, 200000), rng.uniform(-2, 2, 200000), rng.normal(0, 1e-3, 50000),
+                        rng.uniform(-1100, 1100, 20000), [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, 709.79, -745.2, -708.4]])
+    y = eng.unary_dev("exp", torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = np.array([oracle.lib.pvv_oracle_exp(v) for v in x])
+    assert_bit_equal(ref, y, "exp")
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 200000)), rng.uniform(0.9, 1.1, 200000), rng.uniform(0, 3, 50000),
+                        [0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310, 1.0, 2.2250738585072014e-308]])
+    y = eng.unary_dev("log", torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = np.array([oracle.lib.pvv_oracle_log(v) for v in x])
+    assert_bit_equal(ref, y, "log")
+
+
+@pytest.mark.parametrize("name", ["erfcx", "erfc", "norm_cdf", "inverse_norm_cdf"])
+def test_device_special_functions(eng, oracle, name):
+    import torch
+    rng = np.random.default_rng(12)
+    if name == "inverse_norm_cdf":
+        x = np.concatenate([rng.uniform(0, 1, 100000), np.exp(rng.uniform(-700, 0, 50000)), [0.0, 1.0, 0.5, -1.0, 2.0]])
+    else:
+        x = np.concatenate([rng.uniform(-30, 30, 150000), rng.uniform(-1, 1, 50000), rng.uniform(-1e5, 1e9, 1000), [0.0, np.nan, np.inf, -np.inf]])
+    y = eng.unary_dev(name, torch.from_numpy(x).cuda()).cpu().numpy()
+    fn = getattr(oracle.lib, "pvv_oracle_" + name)
+    ref = np.array([fn(v) for v in x])
+    assert_bit_equal(ref, y, name)
+
+
+@pytest.mark.parametrize("chain", ["cfg2", "wide", "edge"])
+def test_prices_golden(eng, golden, chain):
+    g = golden(chain)
+    for model, tag in (("black_scholes", "bs"), ("black_scholes_merton", "bsm"), ("black", "black")):
+        assert_bit_equal(g[f"price_{tag}"], run_price(eng, model, g), f"{chain} {model}")
+
+
+@pytest.mark.parametrize("chain", ["cfg2", "wide", "edge"])
+def test_fd_greeks_golden(eng, golden, chain):
+    g = golden(chain)
+    for model, tag in (("black_scholes", "bs"), ("black_scholes_merton", "bsm")):
+        o = run_greeks(eng, model, g, with_price=True)
+        assert_bit_equal(g[f"price_{tag}"], o["price"], f"{chain} fused price {model}")
+        for k in GREEKS:
+            assert_bit_equal(g[f"{k}_{tag}"], o[k], f"{chain} {k} {model}")
+            rel = np.abs(o[k] - g[f"{k}_{tag}"]) / np.maximum(np.abs(g[f"{k}_{tag}"]), 1e-300)
+            assert np.nanmax(np.where(np.isfinite(rel), rel, 0)) <= 1e-12
+        # each greek on its own evaluates only its stencil points and must give the same bits
+        for k in GREEKS:
+            assert_bit_equal(o[k], run_greeks(eng, model, g, want=(k,))[k], f"{chain} single {k}")
+
+
+@pytest.mark.parametrize("model,tag", [("black_scholes_merton", "bsm"), ("black_scholes", "bs"), ("black", "black")])
+@pytest.mark.parametrize("on_error", ["warn", "ignore"])
+def test_iv_golden_cfg3(eng, oracle, golden, model, tag, on_error):
+    g = golden("cfg3")
+    iv, status, zde = run_iv(eng, model, g, g["price"], mask=(on_error != "ignore"))
+    ref = g[f"iv_{tag}_{on_error}_glibc"]
+    assert zde == -1
+    assert (np.isnan(iv) == np.isnan(ref)).all(), "NaN positions differ"
+    inf = np.isinf(ref)
+    assert (np.isinf(iv) == inf).all() and (iv[inf] == ref[inf]).all()
+    fin = np.isfinite(ref)
+    assert np.abs(iv[fin] - ref[fin]).max() <= 1e-10
+    _, st_ref, _, br = oracle.iv(model, g["price"], g["S"], g["K"], g["t"], g["r"], g["flag"], g["q"], mask_errors=(on_error != "ignore"),
+                                 want_branch=True)
+    assert (status == st_ref).all(), "status bytes differ from the oracle"
+    not_lowest = br != 1
+    assert_bit_equal(ref[not_lowest], iv[not_lowest], "IV outside the lowest branch")
+    assert (iv == ref)[fin].mean() > 0.95
+
+
+def test_iv_loop_and_edges(eng, golden):
+    for chain in ("cfg2", "wide"):
+        g = golden(chain)
+        z = dict(g, r=np.zeros_like(g["r"]))
+        iv, status, zde = run_iv(eng, "black", z, g["price_black"], mask=False)
+        ref = g["ivloop_black"]
+        assert zde == -1
+        assert (np.isnan(iv) == np.isnan(ref)).all()
+        fin = np.isfinite(ref) & np.isfinite(iv)
+        assert (np.isfinite(ref) == np.isfinite(iv)).all()
+        assert np.abs(iv[fin] - ref[fin]).max() <= 1e-10, chain
+    g = golden("edge")
+    k = g["ivloop_keep"]
+    gk = {n: g[n][k] for n in ("flag", "S", "K", "t", "r", "q", "sigma", "price")}
+    for on_error in ("warn", "ignore"):
+        iv, status, zde = run_iv(eng, "black_scholes_merton", gk, gk["price"], mask=(on_error != "ignore"))
+        ref = g[f"iv_bsm_{on_error}_glibc"]
+        assert (np.isnan(iv) == np.isnan(ref)).all()
+        fin = np.isfinite(ref)
+        assert (np.isfinite(iv) == fin).all()
+        assert np.abs(iv[fin] - ref[fin]).max() <= 1e-10
+
+
+def test_reference_regression_table(eng, golden):
+    """The reference's own test_entrypoints.py:24-152 assertions on its 101-row JSON table."""
+    from numpy.testing import assert_array_almost_equal
+    g = golden("cfg1_json")
+    n = g["S"].size
+    for fl, tag, colname, D, G, V in ((1, "c", "bs_call", "CD", "CG", "CV"), (-1, "p", "bs_put", "PD", "PG", "PV")):
+        c = dict(flag=np.full(n, fl, dtype=np.int8), S=g["S"], K=g["K"], t=g["t"], r=g["R"], sigma=g["v"], q=np.zeros(n))
+        p = run_price(eng, "black_scholes", c)
+        assert_array_almost_equal(p, g[colname])
+        assert_array_almost_equal(run_price(eng, "black_scholes_merton", c), g[colname])
+        o = run_greeks(eng, "black_scholes", c)
+        assert_array_almost_equal(o["delta"], g[D])
+        assert_array_almost_equal(o["gamma"], g[G])
+        assert_array_almost_equal(o["vega"], g[V] * .01, 3)
+        assert_bit_equal(g[f"ref_{tag}_price_bs"], p)
+        for k in GREEKS:
+            assert_bit_equal(g[f"ref_{tag}_{k}_bs"], o[k], k)
+        iv, status, _ = run_iv(eng, "black_scholes", c, p)
+        ref = g[f"ref_{tag}_ivroundtrip_glibc"]
+        assert (np.isnan(iv) == np.isnan(ref)).all()
+        assert np.nanmax(np.abs(iv - ref)) <= 1e-10
+        ok = np.isclose(g["v"], iv, atol=1e-2)
+        ok[~ok] = iv[~ok] == 0
+        assert ok.all()
+
+
+def test_zero_division_is_reported(eng):
+    one = lambda v: (np.array([v], dtype=np.float64), 1)  # noqa: E731
+    f = (np.array([1], dtype=np.int8), 1)
+    with pytest.raises(ZeroDivisionError):
+        eng.price("black_scholes", 1, f, one(100.0), one(0.0), one(0.5), one(0.01), None, one(0.2))
+    for kw in (dict(t=0.0), dict(K=0.0), dict(S=0.0)):
+        b = dict(price=5.0, S=100.0, K=100.0, t=0.5, r=0.01)
+        b.update(kw)
+        iv, status, zde = eng.iv("black_scholes", 1, f, one(b["price"]), one(b["S"]), one(b["K"]), one(b["t"]), one(b["r"]), None)
+        assert zde == 0 and status[0] & 4
+    # the index reported is the first offending contract, also across pipeline chunks
+    n = 50000
+    K = np.full(n, 100.0)
+    K[[31337, 40000]] = 0.0
+    ctx = eng.get_ctx(chunk=8192, nstreams=3)
+    iv, status, zde = eng.iv("black_scholes", n, (np.ones(n, dtype=np.int8), 1), (np.full(n, 5.0), 1), (np.full(n, 100.0), 1), (K, 1),
+                             (np.full(n, 0.5), 1), (np.full(n, 0.01), 1), None, ctx=ctx)
+    assert zde == 31337
+    assert np.flatnonzero(status & 4).tolist() == [31337, 40000]
+
+
+def test_broadcast_scalars_and_chunking(eng, oracle, golden):
+    """stride-0 columns and a multi-chunk pipeline give the same bits as one dense launch."""
+    g = golden("cfg2")
+    n = g["S"].size
+    ctx = eng.get_ctx(chunk=1000, nstreams=3)  # 5 chunks, ragged tail
+    r0, s0 = 0.03, 0.25
+    out = eng.greeks("black_scholes", n, col(g["flag"]), col(g["S"]), col(g["K"]), col(g["t"]), (np.array([r0]), 0), None,
+                     (np.array([s0]), 0), with_price=True, ctx=ctx)
+    ref, _ = oracle.greeks("black_scholes", g["flag"], g["S"], g["K"], g["t"], r0, s0)
+    for k in ref:
+        assert_bit_equal(ref[k], out[k], k)
+    # empty call
+    e = np.empty(0)
+    assert eng.price("black_scholes", 0, (np.empty(0, dtype=np.int8), 1), (e, 1), (e, 1), (e, 1), (e, 1), None, (e, 1)).size == 0
+
+
+def test_device_pointer_entry_points(eng, oracle, golden):
+    import torch
+    g = golden("cfg3")
+    n = g["S"].size
+    d = {k: torch.from_numpy(np.ascontiguousarray(g[k])).cuda() for k in ("flag", "S", "K", "t", "r", "sigma", "q", "price")}
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    eng.price_dev("black_scholes_merton", n, d["flag"], d["S"], d["K"], d["t"], d["r"], d["q"], d["sigma"], out)
+    ref, _ = oracle.price("black_scholes_merton", g["flag"], g["S"], g["K"], g["t"], g["r"], g["sigma"], g["q"])
+    assert_bit_equal(ref, out.cpu().numpy())
+    # K4: IV then greeks at the solved vol; greeks are checked against the oracle evaluated at the
+    # GPU's own IV (bit-exact), IV against the oracle's (1e-10)
+    iv = torch.empty(n, dtype=torch.float64, device="cuda")
+    st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    outs = {k: torch.empty(n, dtype=torch.float64, device="cuda") for k in GREEKS}
+    zde = eng.new_zde_word("cuda")
+    eng.iv_greeks_dev("black_scholes_merton", n, d["flag"], d["price"], d["S"], d["K"], d["t"], d["r"], d["q"], iv, st, outs, first_zde=zde)
+    torch.cuda.synchronize()
+    assert zde.item() == np.iinfo(np.int64).max
+    iv_h = iv.cpu().numpy()
+    ref_o, st_ref, _ = oracle.iv_greeks("black_scholes_merton", g["price"], g["S"], g["K"], g["t"], g["r"], g["flag"], g["q"])
+    assert (st.cpu().numpy() == st_ref).all()
+    assert (np.isnan(iv_h) == np.isnan(ref_o["iv"])).all()
+    assert np.nanmax(np.abs(iv_h - ref_o["iv"])) <= 1e-10
+    gref, _ = oracle.greeks("black_scholes_merton", g["flag"], g["S"], g["K"], g["t"], g["r"], iv_h, g["q"])
+    for k in GREEKS:
+        assert_bit_equal(gref[k], outs[k].cpu().numpy(), f"fused {k}")
