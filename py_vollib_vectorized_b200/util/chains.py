@@ -19,10 +19,9 @@ def chain_cfg2(n, seed=0):
     return dict(flag=flag, S=S, K=K, t=t, r=r, sigma=sigma, q=q)
 
 
-def chain_cfg3(n, seed=1, oracle=None, pricer=None):
+def chain_cfg3(n, seed=1, pricer=None):
     """cfg 3: BSM implied-vol chain with deep-OTM, short-expiry, below-intrinsic, above-maximum
-    and t<0 strata.  `pricer(flag,S,K,t,r,sigma,q) -> price` (BSM) supplies the clean prices
-    (an `oracle` object from oracle/ is accepted for the CPU-side scripts)."""
+    and t<0 strata.  `pricer(flag,S,K,t,r,sigma,q) -> price` (BSM) supplies the clean prices."""
     c = chain_cfg2(n, seed)
     rng = np.random.default_rng(seed + 1000)
     u = rng.random(n)
@@ -38,8 +37,7 @@ def chain_cfg3(n, seed=1, oracle=None, pricer=None):
     F = S[deep] * np.exp((r[deep] - q[deep]) * t[deep])
     K[deep] = F * np.exp(np.where(flag[deep] > 0, m, -m))
     if pricer is None:
-        def pricer(flag, S, K, t, r, sigma, q):
-            return oracle.price("black_scholes_merton", flag, S, K, t, r, sigma, q, threads=oracle.max_threads)[0]
+        raise ValueError("chain_cfg3 needs a BSM pricer callable")
     price = np.array(pricer(flag, S, K, t, r, sigma, q), dtype=np.float64)
     F = S * np.exp((r - q) * t)
     D = np.exp(-r * t)

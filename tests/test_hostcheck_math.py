@@ -1,0 +1,86 @@
+"""CPU tier: the PRODUCT's device math header (csrc/pvv_math.cuh) compiled for the host by
+tests/native/host_selfcheck.cpp, against the golden vectors generated from the reference and the
+host libm.  This is the same source the kernels compile, so it pins the CUDA arithmetic (operation
+order, constants, glibc-exact exp/log) before a GPU is involved."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from tests.util import assert_bit_equal
+
+
+@pytest.fixture(scope="module")
+def H():
+    import __graft_entry__ as g
+    lib = ctypes.CDLL(g.build_hostcheck())
+    for n in ("pvvh_exp", "pvvh_log", "pvvh_const"):
+        getattr(lib, n).restype = ctypes.c_double
+    lib.pvvh_exp.argtypes = [ctypes.c_double]
+    lib.pvvh_log.argtypes = [ctypes.c_double]
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_constants(H):
+    import sys
+    eps = sys.float_info.epsilon
+    r16 = math.sqrt(math.sqrt(math.sqrt(math.sqrt(eps))))
+    want = [math.sqrt(eps), math.sqrt(math.sqrt(eps)), r16, 2 * r16, math.sqrt(sys.float_info.min), math.sqrt(sys.float_info.max),
+            -(1 - math.sqrt(eps)), 2 / (eps * eps), -1 / math.sqrt(eps), 0.01 ** 2.]
+    for i, w in enumerate(want):
+        assert H.pvvh_const(i) == w, i
+
+
+def test_exp_log_bit_identical_to_host_libm(H):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-745, 710, 100000), rng.uniform(-2, 2, 100000), rng.normal(0, 1e-3, 30000),
+                        rng.uniform(-1100, 1100, 20000), [0.0, -0.0, np.inf, -np.inf, 1e-300, -1e-300, 709.782712893384, 709.79, -745.2, -745.13, -708.4]])
+    y = np.empty_like(x)
+    H.pvvh_exp_array(x.size, P(x), P(y))
+    ref = np.array([math.exp(v) if v < 709.7827128933841 else math.inf for v in x])
+    assert_bit_equal(ref, y, "exp")
+    assert math.isnan(H.pvvh_exp(math.nan))
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 100000)), rng.uniform(0.9, 1.1, 100000), rng.uniform(1e-3, 3, 30000),
+                        [5e-324, 1e-310, 1.0, 2.2250738585072014e-308, np.inf]])
+    y = np.empty_like(x)
+    H.pvvh_log_array(x.size, P(x), P(y))
+    ref = np.array([math.log(v) if math.isfinite(v) else v for v in x])
+    assert_bit_equal(ref, y, "log")
+    assert H.pvvh_log(0.0) == -math.inf and math.isnan(H.pvvh_log(-1.0)) and math.isnan(H.pvvh_log(math.nan))
+
+
+@pytest.mark.parametrize("chain", ["cfg2", "wide", "edge"])
+def test_prices_and_greeks_bit_identical_to_reference(H, golden, chain):
+    g = golden(chain)
+    n = g["S"].size
+    c = {k: np.ascontiguousarray(g[k]) for k in ("flag", "S", "K", "t", "r", "q", "sigma")}
+    st = np.empty(n, dtype=np.uint8)
+    for m, tag in ((0, "black"), (1, "bs"), (2, "bsm")):
+        out = np.empty(n)
+        H.pvvh_price(m, n, P(c["flag"]), P(c["S"]), P(c["K"]), P(c["t"]), P(c["r"]), P(c["q"]), P(c["sigma"]), P(out), P(st))
+        assert_bit_equal(g[f"price_{tag}"], out, f"{chain} price {tag}")
+        assert not st.any()
+    for m, tag in ((1, "bs"), (2, "bsm")):
+        out = np.empty((n, 6))
+        H.pvvh_greeks(m, n, P(c["flag"]), P(c["S"]), P(c["K"]), P(c["t"]), P(c["r"]), P(c["q"]), P(c["sigma"]), P(out), P(st))
+        for i, k in enumerate(("price", "delta", "gamma", "theta", "rho", "vega")):
+            assert_bit_equal(g[f"{k}_{tag}"], out[:, i], f"{chain} {k} {tag}")
+
+
+@pytest.mark.parametrize("on_error", ["warn", "ignore"])
+def test_iv_bit_identical_to_reference(H, golden, on_error):
+    g = golden("cfg3")
+    n = g["S"].size
+    c = {k: np.ascontiguousarray(g[k]) for k in ("flag", "S", "K", "t", "r", "q", "price")}
+    for m, tag in ((0, "black"), (1, "bs"), (2, "bsm")):
+        iv, st, br = np.empty(n), np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.int8)
+        H.pvvh_iv(m, n, P(c["flag"]), P(c["price"]), P(c["S"]), P(c["K"]), P(c["t"]), P(c["r"]), P(c["q"]), int(on_error != "ignore"),
+                  P(iv), P(st), P(br))
+        # on the host pow() is glibc's too, so even the lowest branch is bit-identical
+        assert_bit_equal(g[f"iv_{tag}_{on_error}_glibc"], iv, f"cfg3 IV {tag} {on_error}")
+        assert set(np.unique(br)) >= {1, 2, 3}
