@@ -18,6 +18,7 @@
 
 #include "../../include/pvv.h"
 #include "pvv_math.cuh"
+#include "pvv_tile.cuh"
 
 namespace {
 
@@ -36,20 +37,57 @@ __device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
 }
 
 // ---- K1: price --------------------------------------------------------------------------------
+// Tile = 1024 contracts per CTA of 128 threads (8 per thread, strided so that global accesses stay
+// coalesced).  P1 stages each contract's (x, s, sqrt(F)sqrt(K), intrinsic, deflater) in shared
+// memory, P2 evaluates b(x, s) in region-sorted order (pvv_tile.cuh), P3 stores the prices.
+constexpr int kTileThreads = 128;
+constexpr int kItemsPerThread = 8;
+constexpr int kTileItems = kTileThreads * kItemsPerThread;
+
 template <int MODEL>
-__global__ void __launch_bounds__(kBlock) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
-                                                       const double *__restrict__ K, const double *__restrict__ t,
-                                                       const double *__restrict__ r, const double *__restrict__ q,
-                                                       const double *__restrict__ sigma, Strides st, double *__restrict__ price,
-                                                       long long *first_zde, long long base) {
-    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const double f = (double)flag[i * st.s[0]];
-    const double rr = (MODEL == pvv::MODEL_BLACK) ? 0.0 : r[i * st.s[4]];
-    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
-    unsigned status = 0;
-    price[i] = pvv::price_model<MODEL>(f, S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], rr, sigma[i * st.s[6]], qq, status);
-    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+__global__ void __launch_bounds__(kTileThreads) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+                                                             const double *__restrict__ K, const double *__restrict__ t,
+                                                             const double *__restrict__ r, const double *__restrict__ q,
+                                                             const double *__restrict__ sigma, Strides st, double *__restrict__ price,
+                                                             long long *first_zde, long long base) {
+    __shared__ pvv::PriceItems<kTileItems> items;
+    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    const int tid = threadIdx.x;
+    const long long tile_base = (long long)blockIdx.x * kTileItems;
+#pragma unroll 1
+    for (int j = 0; j < kItemsPerThread; ++j) {
+        const int item = j * kTileThreads + tid;
+        const long long i = tile_base + item;
+        if (i >= n) {
+            pvv::stage_null_item(items, item);
+            continue;
+        }
+        const double f = (double)flag[i * st.s[0]];
+        const double Si = S[i * st.s[1]], Ki = K[i * st.s[2]], ti = t[i * st.s[3]], sg = sigma[i * st.s[6]];
+        unsigned status = 0;
+        double F = Si, D = 1.0;
+        if (MODEL != pvv::MODEL_BLACK) {
+            const double ri = r[i * st.s[4]];
+            D = pvv::exp_g(-ri * ti);
+            if (MODEL == pvv::MODEL_BLACK_SCHOLES) {
+                if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
+                F = Si / D;
+            } else {
+                F = Si * pvv::exp_g((ri - q[i * st.s[5]]) * ti);
+            }
+        }
+        pvv::stage_price_item(items, item, f, F, Ki, sqrt(Ki), sg * sqrt(ti), D, status);
+        if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    }
+    int zde_item = -1;
+    pvv::eval_price_items<kTileThreads, kItemsPerThread, MODEL != pvv::MODEL_BLACK>(items, ts, zde_item);
+    if (zde_item >= 0) note_zde(first_zde, base + tile_base + zde_item);
+#pragma unroll
+    for (int j = 0; j < kItemsPerThread; ++j) {
+        const int item = j * kTileThreads + tid;
+        const long long i = tile_base + item;
+        if (i < n) price[i] = items.x[item];
+    }
 }
 
 // ---- K2: finite-difference greeks ---------------------------------------------------------------
@@ -108,29 +146,115 @@ __device__ __forceinline__ Greeks greeks_stencil(double flag, double S, double K
     return g;
 }
 
+// Tiled K2: 128 contracts per CTA, one per thread, the 8 stencil points are 8 work items per thread
+// (item = e * 128 + tid).  P1 shares every bit-neutral sub-expression between stencil points
+// (SURVEY.md 8(a) G7): exp(-r t) once for E0,E1,E2,E6,E7; F, ln(F/K), sqrt(F) once for E0,E6,E7;
+// sqrt(K) once; sqrt(t) twice.  P2 = region-sorted evaluation; P3 = the difference quotients.
 template <int MODEL>
-__global__ void __launch_bounds__(kBlock) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
-                                                        const double *__restrict__ K, const double *__restrict__ t,
-                                                        const double *__restrict__ r, const double *__restrict__ q,
-                                                        const double *__restrict__ sigma, Strides st, double *__restrict__ price,
-                                                        double *__restrict__ delta, double *__restrict__ gamma,
-                                                        double *__restrict__ theta, double *__restrict__ rho, double *__restrict__ vega,
-                                                        long long *first_zde, long long base) {
-    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+                                                              const double *__restrict__ K, const double *__restrict__ t,
+                                                              const double *__restrict__ r, const double *__restrict__ q,
+                                                              const double *__restrict__ sigma, Strides st, double *__restrict__ price,
+                                                              double *__restrict__ delta, double *__restrict__ gamma,
+                                                              double *__restrict__ theta, double *__restrict__ rho, double *__restrict__ vega,
+                                                              long long *first_zde, long long base) {
+    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
+    __shared__ pvv::PriceItems<kTileItems> items;
+    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    const int tid = threadIdx.x;
+    const long long i = (long long)blockIdx.x * kTileThreads + tid;
     const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
                           (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
-    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
-    unsigned status = 0;
-    const Greeks g = greeks_stencil<MODEL>((double)flag[i * st.s[0]], S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], r[i * st.s[4]],
-                                           sigma[i * st.s[6]], qq, want, status);
-    if (price) price[i] = g.price;
-    if (delta) delta[i] = g.delta;
-    if (gamma) gamma[i] = g.gamma;
-    if (theta) theta[i] = g.theta;
-    if (rho) rho[i] = g.rho;
-    if (vega) vega[i] = g.vega;
-    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    // stencil points needed by the requested outputs: 0 base, 1/2 S+-dS, 3 t - 1/365, 4/5 r+-0.01, 6/7 sigma+-0.01
+    unsigned need = 0;
+    if (want & (W_PRICE | W_GAMMA | W_THETA)) need |= 1u;
+    if (want & (W_DELTA | W_GAMMA)) need |= 6u;
+    if (want & W_THETA) need |= 8u;
+    if (want & W_RHO) need |= 0x30u;
+    if (want & W_VEGA) need |= 0xc0u;
+    const double dS = .01;
+    double Si = 0, Ki = 0, ti = 0, f = 1;
+    if (i < n) {
+        f = (double)flag[i * st.s[0]];
+        Si = S[i * st.s[1]];
+        Ki = K[i * st.s[2]];
+        ti = t[i * st.s[3]];
+        const double ri = r[i * st.s[4]], sg = sigma[i * st.s[6]];
+        const double b = BSM ? ri - q[i * st.s[5]] : ri;  // api.py:241: b = r - q on the host side of the reference
+        const double qe = BSM ? ri - b : 0.0;             // _numerical_greeks.py: black_scholes_merton(..., r - b)
+        const double sqrtK = sqrt(Ki), sqrtT = sqrt(ti);
+        unsigned status = 0;
+        double D0 = 0.0, g0 = 0.0;
+#pragma unroll 1
+        for (int e = 0; e < 6; ++e) {
+            const bool wanted = ((need >> e) & 1u) || (e == 0 && (need & 0xc6u));
+            if (!wanted) {
+                pvv::stage_null_item(items, e * kTileThreads + tid);
+                continue;
+            }
+            const double Se = (e == 1) ? Si + dS : ((e == 2) ? Si - dS : Si);
+            const double te = (e == 3) ? ((ti <= 1. / 365.) ? 0.00001 : ti - 1. / 365.) : ti;
+            const double re = (e == 4) ? ri + 0.01 : ((e == 5) ? ri - 0.01 : ri);
+            const double qv = (e == 4) ? ri - b + 0.01 : ((e == 5) ? ri - b - 0.01 : qe);
+            double D, F;
+            if (e == 1 || e == 2) {  // same deflater (and carry factor) as the base point
+                D = D0;
+                F = BSM ? Se * g0 : Se / D0;
+            } else {
+                D = pvv::exp_g(-re * te);
+                if (BSM) {
+                    const double g = pvv::exp_g((re - qv) * te);
+                    F = Se * g;
+                    if (e == 0) g0 = g;
+                } else {
+                    if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
+                    F = Se / D;
+                }
+                if (e == 0) D0 = D;
+            }
+            const double sq = (e == 3) ? sqrt(te) : sqrtT;
+            const int item = e * kTileThreads + tid;
+            pvv::stage_price_item(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
+            if (e == 0) {  // sigma +- 0.01: same forward, only s changes
+#pragma unroll
+                for (int v = 6; v < 8; ++v) {
+                    const int iv_ = v * kTileThreads + tid;
+                    if ((need >> v) & 1u) {
+                        items.x[iv_] = items.x[item];
+                        items.s[iv_] = ((v == 6) ? sg + 0.01 : sg - 0.01) * sq;
+                        items.scale[iv_] = items.scale[item];
+                        items.intr[iv_] = items.intr[item];
+                        items.defl[iv_] = D;
+                    } else {
+                        pvv::stage_null_item(items, iv_);
+                    }
+                }
+                if (!(need & 1u)) pvv::stage_null_item(items, item);  // base point only served as the template
+            }
+        }
+        if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pvv::stage_null_item(items, e * kTileThreads + tid);
+    }
+    int zde_item = -1;
+    pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(items, ts, zde_item);
+    if (zde_item >= 0) note_zde(first_zde, base + (long long)blockIdx.x * kTileThreads + (zde_item % kTileThreads));
+    if (i >= n) return;
+    double p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) p[e] = items.x[e * kTileThreads + tid];
+    if (price) price[i] = p[0];
+    if (ti == 0.0) {
+        if (delta) delta[i] = (Si == Ki) ? (f > 0 ? 0.5 : -0.5) : (Si > Ki ? (f > 0 ? 1.0 : 0.0) : (f > 0 ? 0.0 : -1.0));
+        if (gamma) gamma[i] = (Si == Ki) ? pvv::u2d(0x7ff0000000000000ull) : 0.0;
+    } else {
+        if (delta) delta[i] = (p[1] - p[2]) / (2 * dS);
+        if (gamma) gamma[i] = (p[1] - 2. * p[0] + p[2]) / 0x1.a36e2eb1c432dp-14;  // dS ** 2.
+    }
+    if (theta) theta[i] = p[3] - p[0];
+    if (rho) rho[i] = (p[4] - p[5]) / 2.;
+    if (vega) vega[i] = (p[6] - p[7]) / 2.;
 }
 
 // ---- K3: implied volatility ("Let's be rational") ------------------------------------------------
@@ -227,6 +351,7 @@ __global__ void fp64_probe_kernel(int iters, double *out) {
 }
 
 inline int grid_for(long long n) { return (int)((n + kBlock - 1) / kBlock); }
+inline int grid_tiles(long long n, int per_cta) { return (int)((n + per_cta - 1) / per_cta); }
 
 inline bool fill_strides(const int64_t *stride, Strides &out) {
     for (int i = 0; i < 7; ++i) {
@@ -270,9 +395,9 @@ static int launch_price(int model, int64_t n, const int8_t *flag, const double *
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 0) price_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
-    else if (model == 1) price_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
-    else price_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    if (model == 0) price_kernel<0><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    else if (model == 1) price_kernel<1><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    else price_kernel<2><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
     g_launches++;
     return launch_status();
 }
@@ -286,8 +411,8 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 2) greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
-    else greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    if (model == 2) greeks_kernel<2><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    else greeks_kernel<1><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
     g_launches++;
     return launch_status();
 }
@@ -319,11 +444,11 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
-        iv_greeks_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<0><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else if (model == 1)
-        iv_greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<1><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else
-        iv_greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<2><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     g_launches++;
     return launch_status();
 }
