@@ -37,15 +37,16 @@ __device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
 }
 
 // ---- K1: price --------------------------------------------------------------------------------
-// Tile = 1024 contracts per CTA of 128 threads (8 per thread, strided so that global accesses stay
+// Tile = 1024 contracts per CTA of 256 threads (4 per thread, strided so that global accesses stay
 // coalesced).  P1 stages each contract's (x, s, sqrt(F)sqrt(K), intrinsic, deflater) in shared
 // memory, P2 evaluates b(x, s) in region-sorted order (pvv_tile.cuh), P3 stores the prices.
-constexpr int kTileThreads = 128;
-constexpr int kItemsPerThread = 8;
+constexpr int kTileThreads = 256;
+constexpr int kItemsPerThread = 4;
 constexpr int kTileItems = kTileThreads * kItemsPerThread;
+constexpr int kGreekContracts = kTileItems / 8;  // contracts per CTA of the greeks kernel: 8 stencil points each
 
 template <int MODEL>
-__global__ void __launch_bounds__(kTileThreads) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+__global__ void __launch_bounds__(kTileThreads, 4) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                              const double *__restrict__ K, const double *__restrict__ t,
                                                              const double *__restrict__ r, const double *__restrict__ q,
                                                              const double *__restrict__ sigma, Strides st, double *__restrict__ price,
@@ -146,12 +147,12 @@ __device__ __forceinline__ Greeks greeks_stencil(double flag, double S, double K
     return g;
 }
 
-// Tiled K2: 128 contracts per CTA, one per thread, the 8 stencil points are 8 work items per thread
-// (item = e * 128 + tid).  P1 shares every bit-neutral sub-expression between stencil points
+// Tiled K2: 128 contracts per CTA of 256 threads; the 8 stencil points of a contract are 8 work
+// items (item = e * 128 + c).  Two threads stage one contract (points 0,1,2,6,7 / points 3,4,5).  P1 shares every bit-neutral sub-expression between stencil points
 // (SURVEY.md 8(a) G7): exp(-r t) once for E0,E1,E2,E6,E7; F, ln(F/K), sqrt(F) once for E0,E6,E7;
 // sqrt(K) once; sqrt(t) twice.  P2 = region-sorted evaluation; P3 = the difference quotients.
 template <int MODEL>
-__global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+__global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                               const double *__restrict__ K, const double *__restrict__ t,
                                                               const double *__restrict__ r, const double *__restrict__ q,
                                                               const double *__restrict__ sigma, Strides st, double *__restrict__ price,
@@ -162,7 +163,9 @@ __global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const
     __shared__ pvv::PriceItems<kTileItems> items;
     __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
     const int tid = threadIdx.x;
-    const long long i = (long long)blockIdx.x * kTileThreads + tid;
+    const int c = tid % kGreekContracts;     // contract within the tile
+    const int half = tid / kGreekContracts;  // 0: stencil points 0,1,2 (+6,7); 1: points 3,4,5 (warp-uniform split)
+    const long long i = (long long)blockIdx.x * kGreekContracts + c;
     const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
                           (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
     // stencil points needed by the requested outputs: 0 base, 1/2 S+-dS, 3 t - 1/365, 4/5 r+-0.01, 6/7 sigma+-0.01
@@ -186,10 +189,16 @@ __global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const
         unsigned status = 0;
         double D0 = 0.0, g0 = 0.0;
 #pragma unroll 1
-        for (int e = 0; e < 6; ++e) {
+        for (int k = 0; k < 3; ++k) {
+            const int e = half * 3 + k;
+            const int item = e * kGreekContracts + c;
             const bool wanted = ((need >> e) & 1u) || (e == 0 && (need & 0xc6u));
             if (!wanted) {
-                pvv::stage_null_item(items, e * kTileThreads + tid);
+                pvv::stage_null_item(items, item);
+                if (e == 0) {
+                    pvv::stage_null_item(items, 6 * kGreekContracts + c);
+                    pvv::stage_null_item(items, 7 * kGreekContracts + c);
+                }
                 continue;
             }
             const double Se = (e == 1) ? Si + dS : ((e == 2) ? Si - dS : Si);
@@ -213,12 +222,11 @@ __global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const
                 if (e == 0) D0 = D;
             }
             const double sq = (e == 3) ? sqrt(te) : sqrtT;
-            const int item = e * kTileThreads + tid;
             pvv::stage_price_item(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
             if (e == 0) {  // sigma +- 0.01: same forward, only s changes
 #pragma unroll
                 for (int v = 6; v < 8; ++v) {
-                    const int iv_ = v * kTileThreads + tid;
+                    const int iv_ = v * kGreekContracts + c;
                     if ((need >> v) & 1u) {
                         items.x[iv_] = items.x[item];
                         items.s[iv_] = ((v == 6) ? sg + 0.01 : sg - 0.01) * sq;
@@ -235,22 +243,26 @@ __global__ void __launch_bounds__(kTileThreads) greeks_kernel(long long n, const
         if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) pvv::stage_null_item(items, e * kTileThreads + tid);
+        for (int k = 0; k < 3; ++k) pvv::stage_null_item(items, (half * 3 + k) * kGreekContracts + c);
+        if (half == 0) {
+            pvv::stage_null_item(items, 6 * kGreekContracts + c);
+            pvv::stage_null_item(items, 7 * kGreekContracts + c);
+        }
     }
     int zde_item = -1;
     pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(items, ts, zde_item);
-    if (zde_item >= 0) note_zde(first_zde, base + (long long)blockIdx.x * kTileThreads + (zde_item % kTileThreads));
-    if (i >= n) return;
+    if (zde_item >= 0) note_zde(first_zde, base + (long long)blockIdx.x * kGreekContracts + (zde_item % kGreekContracts));
+    if (i >= n || half != 0) return;
     double p[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) p[e] = items.x[e * kTileThreads + tid];
+    for (int e = 0; e < 8; ++e) p[e] = items.x[e * kGreekContracts + c];
     if (price) price[i] = p[0];
     if (ti == 0.0) {
         if (delta) delta[i] = (Si == Ki) ? (f > 0 ? 0.5 : -0.5) : (Si > Ki ? (f > 0 ? 1.0 : 0.0) : (f > 0 ? 0.0 : -1.0));
         if (gamma) gamma[i] = (Si == Ki) ? pvv::u2d(0x7ff0000000000000ull) : 0.0;
     } else {
-        if (delta) delta[i] = (p[1] - p[2]) / (2 * dS);
-        if (gamma) gamma[i] = (p[1] - 2. * p[0] + p[2]) / 0x1.a36e2eb1c432dp-14;  // dS ** 2.
+        if (delta) delta[i] = pvv::div_by_const(p[1] - p[2], 2 * dS, 1.0 / (2 * dS));
+        if (gamma) gamma[i] = pvv::div_by_const(p[1] - 2. * p[0] + p[2], 0x1.a36e2eb1c432dp-14, 1.0 / 0x1.a36e2eb1c432dp-14);  // dS ** 2.
     }
     if (theta) theta[i] = p[3] - p[0];
     if (rho) rho[i] = (p[4] - p[5]) / 2.;
@@ -411,8 +423,8 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 2) greeks_kernel<2><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
-    else greeks_kernel<1><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    if (model == 2) greeks_kernel<2><<<grid_tiles(n, kGreekContracts), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    else greeks_kernel<1><<<grid_tiles(n, kGreekContracts), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
     g_launches++;
     return launch_status();
 }
@@ -444,11 +456,11 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
-        iv_greeks_kernel<0><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else if (model == 1)
-        iv_greeks_kernel<1><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else
-        iv_greeks_kernel<2><<<grid_tiles(n, kTileThreads), kTileThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     g_launches++;
     return launch_status();
 }
