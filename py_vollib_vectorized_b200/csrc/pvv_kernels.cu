@@ -269,24 +269,125 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
     if (vega) vega[i] = (p[6] - p[7]) / 2.;
 }
 
-// ---- K3: implied volatility ("Let's be rational") ------------------------------------------------
+// ---- K3 / K4: implied volatility ("Let's be rational"), staged over a CTA tile ------------------
+// 512 contracts per CTA, one per thread; the solver state lives in registers.  The solver is run as
+// a sequence of stages for the whole tile; wherever the reference's control flow would diverge,
+// the work is regrouped through shared memory so that warps stay uniform:
+//   B1  b_c = b(x, s_c)              region-sorted batch (pvv_tile.cuh)
+//   B2  b_2 = b(x, s_l or s_h)       region-sorted batch
+//   G   initial guess                contracts sorted by solver branch (lowest / lower-middle /
+//                                    upper-middle / highest), state passed through shared memory
+//   B3, B4  b(x, s) of the two Householder(3) passes, region-sorted batches
+// Per-lane arithmetic is exactly pvv::normalised_iv (pvv_math.cuh), so results are unchanged.
+constexpr int kIvThreads = 512;
+
+struct IvShared {
+    double a[8][kIvThreads];  // batch: a[0] = x -> b, a[1] = s;  guess stage: 8 inputs -> 3 outputs
+    unsigned char zde[kIvThreads];
+    unsigned char mode[kIvThreads];
+    pvv::TileSort<kIvThreads, 1> ts;
+};
+
+__device__ __forceinline__ double nbc_batch(IvShared &sh, double x, double s, bool active, unsigned &st) {
+    const int tid = threadIdx.x;
+    __syncthreads();  // the arrays may still be read by the previous stage
+    sh.a[0][tid] = active ? x : 0.0;
+    sh.a[1][tid] = active ? s : 0.0;  // (0, 0) classifies as R_ZERO and costs nothing
+    sh.zde[tid] = 0;
+    pvv::tile_sort(sh.ts, [&](int item) { return pvv::nbc_classify(sh.a[0][item], sh.a[1][item]); });
+    const unsigned e = sh.ts.order[tid];
+    const int item = e & 0xfffu, region = e >> 12;
+    unsigned st2 = 0;
+    const double b = pvv::nbc_eval(region, sh.a[0][item], sh.a[1][item], st2);
+    sh.a[0][item] = b;
+    if (st2) sh.zde[item] = 1;
+    __syncthreads();
+    if (sh.zde[tid]) st |= pvv::ST_ZERO_DIVISION;
+    return sh.a[0][tid];
+}
+
+// The solver for one tile.  `active` = beta > 0 (else the reference returns 0 without solving).
+__device__ __forceinline__ double iv_tile_solve(IvShared &sh, double beta, double x, bool valid, unsigned &st) {
+    const int tid = threadIdx.x;
+    const bool active = valid && !(beta <= 0);
+    const double b_max = pvv::exp_g(0.5 * x);
+    const double s_c = sqrt(fabs(2 * x));
+    const double b_c = nbc_batch(sh, x, s_c, active, st);
+    const double v_c = pvv::normalised_vega(x, s_c);
+    const double s_2 = pvv::iv_second_node(beta, b_max, s_c, b_c, v_c);
+    const double b_2 = nbc_batch(sh, x, s_2, active, st);
+    // initial guess, contracts regrouped by branch
+    const int br = active ? pvv::iv_branch(beta, b_c, b_2) : pvv::IV_DONE;
+    __syncthreads();
+    sh.a[0][tid] = x;
+    sh.a[1][tid] = beta;
+    sh.a[2][tid] = b_max;
+    sh.a[3][tid] = s_c;
+    sh.a[4][tid] = b_c;
+    sh.a[5][tid] = v_c;
+    sh.a[6][tid] = s_2;
+    sh.a[7][tid] = b_2;
+    pvv::tile_sort(sh.ts, [&](int) { return br; });
+    {
+        const unsigned e = sh.ts.order[tid];
+        const int item = e & 0xfffu, branch = e >> 12;
+        if (branch != pvv::IV_DONE) {
+            const pvv::IvState g = pvv::iv_initial_guess(branch, sh.a[0][item], sh.a[1][item], sh.a[2][item], sh.a[3][item], sh.a[4][item],
+                                                         sh.a[5][item], sh.a[6][item], sh.a[7][item]);
+            sh.a[0][item] = g.s;
+            sh.a[1][item] = g.s_left;
+            sh.a[2][item] = g.s_right;
+            sh.mode[item] = (unsigned char)g.mode;
+        }
+    }
+    __syncthreads();
+    pvv::IvState o;
+    o.s = sh.a[0][tid];
+    o.s_left = sh.a[1][tid];
+    o.s_right = sh.a[2][tid];
+    o.mode = sh.mode[tid];
+    double ds = -DBL_MAX;
+    bool running = active;
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        if (running) running = pvv::iv_iteration_head(it, ds, o);
+        const double b = nbc_batch(sh, x, o.s, running, st);
+        if (running) ds = pvv::iv_iteration_tail(x, beta, b_max, b, o);
+    }
+    return active ? o.s : 0.0;
+}
+
 template <int MODEL>
-__global__ void __launch_bounds__(kBlock) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
-                                                    const double *__restrict__ S, const double *__restrict__ K,
-                                                    const double *__restrict__ t, const double *__restrict__ r,
-                                                    const double *__restrict__ q, Strides st, int mask_errors, double *__restrict__ iv,
-                                                    uint8_t *__restrict__ status_out, long long *first_zde, long long base) {
-    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+__global__ void __launch_bounds__(kIvThreads, 2) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
+                                                           const double *__restrict__ S, const double *__restrict__ K,
+                                                           const double *__restrict__ t, const double *__restrict__ r,
+                                                           const double *__restrict__ q, Strides st, int mask_errors,
+                                                           double *__restrict__ iv, uint8_t *__restrict__ status_out, long long *first_zde,
+                                                           long long base) {
+    __shared__ IvShared sh;
+    const long long i = (long long)blockIdx.x * kIvThreads + threadIdx.x;
+    const bool valid = i < n;
     unsigned status = 0;
-    iv[i] = pvv::implied_vol<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
-                                    r[i * st.s[5]], qq, mask_errors != 0, status);
+    pvv::IvFront fr;
+    fr.beta = 0.0;
+    fr.x = 0.0;
+    fr.sqrt_t = 1.0;
+    if (valid) {
+        const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+        fr = pvv::iv_front<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
+                                  r[i * st.s[5]], qq, status);
+    }
+    const double s = iv_tile_solve(sh, fr.beta, fr.x, valid, status);
+    if (!valid) return;
+    double vol = s / fr.sqrt_t;
+    if (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) vol = pvv::u2d(0x7ff8000000000000ull);
+    iv[i] = vol;
     if (status_out) status_out[i] = (uint8_t)status;
     if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
 }
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
+// (straight-line per-thread form for now; the staged version shares iv_tile_solve with K3)
 template <int MODEL>
 __global__ void __launch_bounds__(kBlock) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
                                                            const double *__restrict__ S, const double *__restrict__ K,
@@ -438,9 +539,9 @@ static int launch_iv(int model, int64_t n, const int8_t *flag, const double *pri
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 0) iv_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
-    else if (model == 1) iv_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
-    else iv_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    if (model == 0) iv_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    else if (model == 1) iv_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    else iv_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
     g_launches++;
     return launch_status();
 }
