@@ -22,7 +22,6 @@
 
 namespace {
 
-using pvv::Greeks;
 
 std::atomic<long long> g_launches{0};
 
@@ -80,9 +79,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) price_kernel(long long n, con
         pvv::stage_price_item(items, item, f, F, Ki, sqrt(Ki), sg * sqrt(ti), D, status);
         if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     }
-    int zde_item = -1;
-    pvv::eval_price_items<kTileThreads, kItemsPerThread, MODEL != pvv::MODEL_BLACK>(items, ts, zde_item);
-    if (zde_item >= 0) note_zde(first_zde, base + tile_base + zde_item);
+    pvv::eval_price_items<kTileThreads, kItemsPerThread, MODEL != pvv::MODEL_BLACK>(
+        items, ts, [&](int item) { note_zde(first_zde, base + tile_base + item); });
 #pragma unroll
     for (int j = 0; j < kItemsPerThread; ++j) {
         const int item = j * kTileThreads + tid;
@@ -92,82 +90,16 @@ __global__ void __launch_bounds__(kTileThreads, 4) price_kernel(long long n, con
 }
 
 // ---- K2: finite-difference greeks ---------------------------------------------------------------
-// The eight stencil points are evaluated by ONE loop body (code for a price exists once in the
-// kernel; the instruction cache matters more here than unrolling), skipping points no requested
-// output needs.  `want` bits: 1 price, 2 delta, 4 gamma, 8 theta, 16 rho, 32 vega.
+// `want` bits: 1 price, 2 delta, 4 gamma, 8 theta, 16 rho, 32 vega (stencil points nobody needs are
+// staged as null items and cost nothing).
 enum : unsigned { W_PRICE = 1, W_DELTA = 2, W_GAMMA = 4, W_THETA = 8, W_RHO = 16, W_VEGA = 32 };
 
-template <int MODEL>
-__device__ __forceinline__ Greeks greeks_stencil(double flag, double S, double K, double t, double r, double sigma, double q, unsigned want,
-                                                 unsigned &status) {
-    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
-    const double dS = .01;
-    const double b = BSM ? r - q : r;     // api.py:241 (host side of the reference)
-    const double qe = BSM ? r - b : 0.0;  // _numerical_greeks.py: black_scholes_merton(..., r - b)
-    const bool t0 = (t == 0.0);
-    // which stencil points are needed: 0 base, 1/2 S+-dS, 3 theta, 4/5 r+-0.01, 6/7 sigma+-0.01
-    unsigned need = 0;
-    if (want & (W_PRICE | W_GAMMA | W_THETA)) need |= 1u;
-    if (want & (W_DELTA | W_GAMMA)) need |= t0 ? 0u : 6u;
-    if (want & W_THETA) need |= 8u;
-    if (want & W_RHO) need |= 0x30u;
-    if (want & W_VEGA) need |= 0xc0u;
-    double p[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) p[e] = 0.0;
-#pragma unroll 1
-    for (int e = 0; e < 8; ++e) {
-        if (!((need >> e) & 1u)) continue;
-        double Se = S, te = t, re = r, se = sigma, qv = qe;
-        if (e == 1) Se = S + dS;
-        if (e == 2) Se = S - dS;
-        if (e == 3) te = (t <= 1. / 365.) ? 0.00001 : t - 1. / 365.;
-        if (e == 4) { re = r + 0.01; qv = BSM ? r - b + 0.01 : 0.0; }
-        if (e == 5) { re = r - 0.01; qv = BSM ? r - b - 0.01 : 0.0; }
-        if (e == 6) se = sigma + 0.01;
-        if (e == 7) se = sigma - 0.01;
-        const double v = pvv::price_model<MODEL>(flag, Se, K, te, re, se, qv, status);
-        // static indexing keeps p[] in registers
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j == e) p[j] = v;
-    }
-    Greeks g;
-    g.price = p[0];
-    if (t0) {
-        g.delta = (S == K) ? (flag > 0 ? 0.5 : -0.5) : (S > K ? (flag > 0 ? 1.0 : 0.0) : (flag > 0 ? 0.0 : -1.0));
-        g.gamma = (S == K) ? pvv::u2d(0x7ff0000000000000ull) : 0.0;
-    } else {
-        g.delta = (p[1] - p[2]) / (2 * dS);
-        g.gamma = (p[1] - 2. * p[0] + p[2]) / 0x1.a36e2eb1c432dp-14;  // dS ** 2.
-    }
-    g.theta = p[3] - p[0];
-    g.rho = (p[4] - p[5]) / 2.;
-    g.vega = (p[6] - p[7]) / 2.;
-    return g;
-}
-
 // Tiled K2: 128 contracts per CTA of 256 threads; the 8 stencil points of a contract are 8 work
-// items (item = e * 128 + c).  Two threads stage one contract (points 0,1,2,6,7 / points 3,4,5).  P1 shares every bit-neutral sub-expression between stencil points
+// items (item = e * 128 + c).  Two threads stage one contract (points 0,1,2,6,7 / points 3,4,5).
+// P1 shares every bit-neutral sub-expression between stencil points
 // (SURVEY.md 8(a) G7): exp(-r t) once for E0,E1,E2,E6,E7; F, ln(F/K), sqrt(F) once for E0,E6,E7;
 // sqrt(K) once; sqrt(t) twice.  P2 = region-sorted evaluation; P3 = the difference quotients.
-template <int MODEL>
-__global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
-                                                              const double *__restrict__ K, const double *__restrict__ t,
-                                                              const double *__restrict__ r, const double *__restrict__ q,
-                                                              const double *__restrict__ sigma, Strides st, double *__restrict__ price,
-                                                              double *__restrict__ delta, double *__restrict__ gamma,
-                                                              double *__restrict__ theta, double *__restrict__ rho, double *__restrict__ vega,
-                                                              long long *first_zde, long long base) {
-    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
-    __shared__ pvv::PriceItems<kTileItems> items;
-    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
-    const int tid = threadIdx.x;
-    const int c = tid % kGreekContracts;     // contract within the tile
-    const int half = tid / kGreekContracts;  // 0: stencil points 0,1,2 (+6,7); 1: points 3,4,5 (warp-uniform split)
-    const long long i = (long long)blockIdx.x * kGreekContracts + c;
-    const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
-                          (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
+__device__ __forceinline__ unsigned stencil_need(unsigned want) {
     // stencil points needed by the requested outputs: 0 base, 1/2 S+-dS, 3 t - 1/365, 4/5 r+-0.01, 6/7 sigma+-0.01
     unsigned need = 0;
     if (want & (W_PRICE | W_GAMMA | W_THETA)) need |= 1u;
@@ -175,84 +107,86 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
     if (want & W_THETA) need |= 8u;
     if (want & W_RHO) need |= 0x30u;
     if (want & W_VEGA) need |= 0xc0u;
+    return need;
+}
+
+// P1 for contract slot c of the tile, done by thread `half` (0: points 0,1,2,6,7; 1: points 3,4,5).
+template <bool BSM>
+__device__ __forceinline__ void stage_greeks(pvv::PriceItems<kTileItems> &items, int c, int half, bool valid, double f, double Si, double Ki,
+                                             double ti, double ri, double sg, double qi, unsigned need, unsigned &status) {
     const double dS = .01;
-    double Si = 0, Ki = 0, ti = 0, f = 1;
-    if (i < n) {
-        f = (double)flag[i * st.s[0]];
-        Si = S[i * st.s[1]];
-        Ki = K[i * st.s[2]];
-        ti = t[i * st.s[3]];
-        const double ri = r[i * st.s[4]], sg = sigma[i * st.s[6]];
-        const double b = BSM ? ri - q[i * st.s[5]] : ri;  // api.py:241: b = r - q on the host side of the reference
-        const double qe = BSM ? ri - b : 0.0;             // _numerical_greeks.py: black_scholes_merton(..., r - b)
-        const double sqrtK = sqrt(Ki), sqrtT = sqrt(ti);
-        unsigned status = 0;
-        double D0 = 0.0, g0 = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < 3; ++k) {
-            const int e = half * 3 + k;
-            const int item = e * kGreekContracts + c;
-            const bool wanted = ((need >> e) & 1u) || (e == 0 && (need & 0xc6u));
-            if (!wanted) {
-                pvv::stage_null_item(items, item);
-                if (e == 0) {
-                    pvv::stage_null_item(items, 6 * kGreekContracts + c);
-                    pvv::stage_null_item(items, 7 * kGreekContracts + c);
-                }
-                continue;
-            }
-            const double Se = (e == 1) ? Si + dS : ((e == 2) ? Si - dS : Si);
-            const double te = (e == 3) ? ((ti <= 1. / 365.) ? 0.00001 : ti - 1. / 365.) : ti;
-            const double re = (e == 4) ? ri + 0.01 : ((e == 5) ? ri - 0.01 : ri);
-            const double qv = (e == 4) ? ri - b + 0.01 : ((e == 5) ? ri - b - 0.01 : qe);
-            double D, F;
-            if (e == 1 || e == 2) {  // same deflater (and carry factor) as the base point
-                D = D0;
-                F = BSM ? Se * g0 : Se / D0;
-            } else {
-                D = pvv::exp_g(-re * te);
-                if (BSM) {
-                    const double g = pvv::exp_g((re - qv) * te);
-                    F = Se * g;
-                    if (e == 0) g0 = g;
-                } else {
-                    if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
-                    F = Se / D;
-                }
-                if (e == 0) D0 = D;
-            }
-            const double sq = (e == 3) ? sqrt(te) : sqrtT;
-            pvv::stage_price_item(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
-            if (e == 0) {  // sigma +- 0.01: same forward, only s changes
-#pragma unroll
-                for (int v = 6; v < 8; ++v) {
-                    const int iv_ = v * kGreekContracts + c;
-                    if ((need >> v) & 1u) {
-                        items.x[iv_] = items.x[item];
-                        items.s[iv_] = ((v == 6) ? sg + 0.01 : sg - 0.01) * sq;
-                        items.scale[iv_] = items.scale[item];
-                        items.intr[iv_] = items.intr[item];
-                        items.defl[iv_] = D;
-                    } else {
-                        pvv::stage_null_item(items, iv_);
-                    }
-                }
-                if (!(need & 1u)) pvv::stage_null_item(items, item);  // base point only served as the template
-            }
-        }
-        if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
-    } else {
+    if (!valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) pvv::stage_null_item(items, (half * 3 + k) * kGreekContracts + c);
         if (half == 0) {
             pvv::stage_null_item(items, 6 * kGreekContracts + c);
             pvv::stage_null_item(items, 7 * kGreekContracts + c);
         }
+        return;
     }
-    int zde_item = -1;
-    pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(items, ts, zde_item);
-    if (zde_item >= 0) note_zde(first_zde, base + (long long)blockIdx.x * kGreekContracts + (zde_item % kGreekContracts));
-    if (i >= n || half != 0) return;
+    const double b = BSM ? ri - qi : ri;   // api.py:241: b = r - q on the host side of the reference
+    const double qe = BSM ? ri - b : 0.0;  // _numerical_greeks.py: black_scholes_merton(..., r - b)
+    const double sqrtK = sqrt(Ki), sqrtT = sqrt(ti);
+    double D0 = 0.0, g0 = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        const int e = half * 3 + k;
+        const int item = e * kGreekContracts + c;
+        const bool wanted = ((need >> e) & 1u) || (e == 0 && (need & 0xc6u));
+        if (!wanted) {
+            pvv::stage_null_item(items, item);
+            if (e == 0) {
+                pvv::stage_null_item(items, 6 * kGreekContracts + c);
+                pvv::stage_null_item(items, 7 * kGreekContracts + c);
+            }
+            continue;
+        }
+        const double Se = (e == 1) ? Si + dS : ((e == 2) ? Si - dS : Si);
+        const double te = (e == 3) ? ((ti <= 1. / 365.) ? 0.00001 : ti - 1. / 365.) : ti;
+        const double re = (e == 4) ? ri + 0.01 : ((e == 5) ? ri - 0.01 : ri);
+        const double qv = (e == 4) ? ri - b + 0.01 : ((e == 5) ? ri - b - 0.01 : qe);
+        double D, F;
+        if (e == 1 || e == 2) {  // same deflater (and carry factor) as the base point
+            D = D0;
+            F = BSM ? Se * g0 : Se / D0;
+        } else {
+            D = pvv::exp_g(-re * te);
+            if (BSM) {
+                const double g = pvv::exp_g((re - qv) * te);
+                F = Se * g;
+                if (e == 0) g0 = g;
+            } else {
+                if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
+                F = Se / D;
+            }
+            if (e == 0) D0 = D;
+        }
+        const double sq = (e == 3) ? sqrt(te) : sqrtT;
+        pvv::stage_price_item(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
+        if (e == 0) {  // sigma +- 0.01: same forward, only s changes
+#pragma unroll
+            for (int v = 6; v < 8; ++v) {
+                const int iv_ = v * kGreekContracts + c;
+                if ((need >> v) & 1u) {
+                    items.x[iv_] = items.x[item];
+                    items.s[iv_] = ((v == 6) ? sg + 0.01 : sg - 0.01) * sq;
+                    items.scale[iv_] = items.scale[item];
+                    items.intr[iv_] = items.intr[item];
+                    items.defl[iv_] = D;
+                } else {
+                    pvv::stage_null_item(items, iv_);
+                }
+            }
+            if (!(need & 1u)) pvv::stage_null_item(items, item);  // base point only served as the template
+        }
+    }
+}
+
+// P3: the difference quotients of _numerical_greeks.py from the eight finished prices of slot c.
+__device__ __forceinline__ void finish_greeks(const pvv::PriceItems<kTileItems> &items, int c, long long i, double f, double Si, double Ki,
+                                              double ti, double *price, double *delta, double *gamma, double *theta, double *rho,
+                                              double *vega) {
+    const double dS = .01;
     double p[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) p[e] = items.x[e * kGreekContracts + c];
@@ -267,6 +201,43 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
     if (theta) theta[i] = p[3] - p[0];
     if (rho) rho[i] = (p[4] - p[5]) / 2.;
     if (vega) vega[i] = (p[6] - p[7]) / 2.;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+                                                                 const double *__restrict__ K, const double *__restrict__ t,
+                                                                 const double *__restrict__ r, const double *__restrict__ q,
+                                                                 const double *__restrict__ sigma, Strides st, double *__restrict__ price,
+                                                                 double *__restrict__ delta, double *__restrict__ gamma,
+                                                                 double *__restrict__ theta, double *__restrict__ rho,
+                                                                 double *__restrict__ vega, long long *first_zde, long long base) {
+    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
+    __shared__ pvv::PriceItems<kTileItems> items;
+    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    const int tid = threadIdx.x;
+    const int c = tid % kGreekContracts;     // contract within the tile
+    const int half = tid / kGreekContracts;  // warp-uniform split of the staging work
+    const long long i = (long long)blockIdx.x * kGreekContracts + c;
+    const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
+                          (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
+    const bool valid = i < n;
+    double Si = 0, Ki = 0, ti = 0, f = 1, ri = 0, sg = 0, qi = 0;
+    if (valid) {
+        f = (double)flag[i * st.s[0]];
+        Si = S[i * st.s[1]];
+        Ki = K[i * st.s[2]];
+        ti = t[i * st.s[3]];
+        ri = r[i * st.s[4]];
+        sg = sigma[i * st.s[6]];
+        if (BSM) qi = q[i * st.s[5]];
+    }
+    unsigned status = 0;
+    stage_greeks<BSM>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, stencil_need(want), status);
+    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(
+        items, ts, [&](int item) { note_zde(first_zde, base + (long long)blockIdx.x * kGreekContracts + (item % kGreekContracts)); });
+    if (!valid || half != 0) return;
+    finish_greeks(items, c, i, f, Si, Ki, ti, price, delta, gamma, theta, rho, vega);
 }
 
 // ---- K3 / K4: implied volatility ("Let's be rational"), staged over a CTA tile ------------------
@@ -387,35 +358,84 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_kernel(long long n, const in
 }
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
-// (straight-line per-thread form for now; the staged version shares iv_tile_solve with K3)
+// One CTA = 512 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2 runs the K2
+// tile machinery four times, 128 contracts (1024 stencil items) at a time, over the same shared
+// memory.  The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
+struct IvGreeksShared {
+    pvv::PriceItems<kTileItems> items;
+    pvv::TileSort<kIvThreads, kTileItems / kIvThreads> ts;
+    double vol[kIvThreads];
+    unsigned char zf[3][kGreekContracts];  // zero-division flags of a sub-tile: staging half 0 / half 1 / evaluation
+};
+union IvGreeksUnion {
+    IvShared iv;
+    IvGreeksShared g;
+};
+
 template <int MODEL>
-__global__ void __launch_bounds__(kBlock) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
-                                                           const double *__restrict__ S, const double *__restrict__ K,
-                                                           const double *__restrict__ t, const double *__restrict__ r,
-                                                           const double *__restrict__ q, Strides st, int mask_errors,
-                                                           double *__restrict__ iv, uint8_t *__restrict__ status_out,
-                                                           double *__restrict__ delta, double *__restrict__ gamma,
-                                                           double *__restrict__ theta, double *__restrict__ rho,
-                                                           double *__restrict__ vega, long long *first_zde, long long base) {
-    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const double f = (double)flag[i * st.s[0]];
-    const double Si = S[i * st.s[2]], Ki = K[i * st.s[3]], ti = t[i * st.s[4]], ri = r[i * st.s[5]];
-    const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+__global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag,
+                                                                  const double *__restrict__ price, const double *__restrict__ S,
+                                                                  const double *__restrict__ K, const double *__restrict__ t,
+                                                                  const double *__restrict__ r, const double *__restrict__ q, Strides st,
+                                                                  int mask_errors, double *__restrict__ iv, uint8_t *__restrict__ status_out,
+                                                                  double *__restrict__ delta, double *__restrict__ gamma,
+                                                                  double *__restrict__ theta, double *__restrict__ rho,
+                                                                  double *__restrict__ vega, long long *first_zde, long long base) {
+    constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
+    __shared__ __align__(16) unsigned char raw[sizeof(IvGreeksUnion)];
+    IvShared &sh = reinterpret_cast<IvGreeksUnion *>(raw)->iv;
+    IvGreeksShared &gs = reinterpret_cast<IvGreeksUnion *>(raw)->g;
+    const int tid = threadIdx.x;
+    const long long tile0 = (long long)blockIdx.x * kIvThreads;
+    const long long i = tile0 + tid;
+    const bool valid = i < n;
     unsigned status = 0;
-    const double vol = pvv::implied_vol<MODEL>(f, price[i * st.s[1]], Si, Ki, ti, ri, qq, mask_errors != 0, status);
-    iv[i] = vol;
+    pvv::IvFront fr;
+    fr.beta = 0.0;
+    fr.x = 0.0;
+    fr.sqrt_t = 1.0;
+    if (valid) {
+        const double qq = BSM ? q[i * st.s[6]] : 0.0;
+        fr = pvv::iv_front<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
+                                  r[i * st.s[5]], qq, status);
+    }
+    const double s = iv_tile_solve(sh, fr.beta, fr.x, valid, status);
+    double vol = s / fr.sqrt_t;
+    if (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) vol = pvv::u2d(0x7ff8000000000000ull);
+    if (valid) iv[i] = vol;
+    __syncthreads();  // the solver's shared arrays are dead from here on
+    gs.vol[tid] = vol;
     const unsigned want = (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) | (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
-    constexpr int GM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? pvv::MODEL_BLACK_SCHOLES_MERTON : pvv::MODEL_BLACK_SCHOLES;
-    unsigned gstatus = 0;
-    const Greeks g = greeks_stencil<GM>(f, Si, Ki, ti, ri, vol, qq, want, gstatus);
-    status |= gstatus & pvv::ST_ZERO_DIVISION;
+    const unsigned need = stencil_need(want);
+#pragma unroll 1
+    for (int sub = 0; sub < kIvThreads / kGreekContracts; ++sub) {
+        __syncthreads();
+        const int c = tid % kGreekContracts, half = tid / kGreekContracts;  // threads >= 256 only help in P2
+        const long long gi = tile0 + sub * kGreekContracts + c;
+        const bool gvalid = gi < n && half < 2;
+        double Si = 0, Ki = 0, ti = 0, f = 1, ri = 0, qi = 0, sg = 0;
+        if (gvalid) {
+            f = (double)flag[gi * st.s[0]];
+            Si = S[gi * st.s[2]];
+            Ki = K[gi * st.s[3]];
+            ti = t[gi * st.s[4]];
+            ri = r[gi * st.s[5]];
+            if (BSM) qi = q[gi * st.s[6]];
+            sg = gs.vol[sub * kGreekContracts + c];
+        }
+        if (half < 2) {
+            unsigned sst = 0;
+            stage_greeks<BSM>(gs.items, c, half, gvalid, f, Si, Ki, ti, ri, sg, qi, need, sst);
+            gs.zf[half][c] = (sst & pvv::ST_ZERO_DIVISION) ? 1 : 0;
+            if (half == 0) gs.zf[2][c] = 0;
+        }
+        pvv::eval_price_items<kIvThreads, kTileItems / kIvThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kGreekContracts] = 1; });
+        if (gvalid && half == 0) finish_greeks(gs.items, c, gi, f, Si, Ki, ti, nullptr, delta, gamma, theta, rho, vega);
+        __syncthreads();  // zf[2] written during the evaluation
+        if (tid / kGreekContracts == sub && (gs.zf[0][c] | gs.zf[1][c] | gs.zf[2][c])) status |= pvv::ST_ZERO_DIVISION;  // owner thread
+    }
+    if (!valid) return;
     if (status_out) status_out[i] = (uint8_t)status;
-    if (delta) delta[i] = g.delta;
-    if (gamma) gamma[i] = g.gamma;
-    if (theta) theta[i] = g.theta;
-    if (rho) rho[i] = g.rho;
-    if (vega) vega[i] = g.vega;
     if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
 }
 
@@ -557,11 +577,11 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
-        iv_greeks_kernel<0><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else if (model == 1)
-        iv_greeks_kernel<1><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     else
-        iv_greeks_kernel<2><<<grid_for(n), kBlock, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        iv_greeks_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
     g_launches++;
     return launch_status();
 }

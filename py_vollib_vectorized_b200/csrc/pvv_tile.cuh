@@ -94,10 +94,9 @@ __device__ __forceinline__ void stage_null_item(PriceItems<T> &it, int item) {
 }
 
 // Evaluate every item of the tile in region-sorted order and finish it to a price (in place, x[]).
-// Returns ST_ZERO_DIVISION in `st` for the items this thread evaluated; `zde_item` receives one
-// such item id (or stays -1).
-template <int NT, int IPT, bool DEFLATE>
-__device__ __forceinline__ void eval_price_items(PriceItems<NT * IPT> &it, TileSort<NT, IPT> &ts, int &zde_item) {
+// `on_zde(item)` is called for every item whose evaluation divided by zero (numba would raise).
+template <int NT, int IPT, bool DEFLATE, class OnZde>
+__device__ __forceinline__ void eval_price_items(PriceItems<NT * IPT> &it, TileSort<NT, IPT> &ts, OnZde on_zde) {
     tile_sort(ts, [&](int item) { return nbc_classify(it.x[item], it.s[item]); });
     const int tid = threadIdx.x;
 #pragma unroll 1
@@ -111,7 +110,7 @@ __device__ __forceinline__ void eval_price_items(PriceItems<NT * IPT> &it, TileS
         double v = (is < 0) ? (-is) + np_maximum(0.0, tv) : np_maximum(is, tv);
         if (DEFLATE) v = v * it.defl[item];
         it.x[item] = v;
-        if (st & ST_ZERO_DIVISION) zde_item = item;
+        if (st & ST_ZERO_DIVISION) on_zde(item);
     }
     __syncthreads();
 }
