@@ -55,10 +55,18 @@ def parse():
     return ap.parse_args()
 
 
-def make_chain(workload, n, seed):
-    from py_vollib_vectorized_b200.util.chains import chain_cfg2
-    c = chain_cfg2(n, seed=seed)
-    return c
+def make_chain(workload, n, seed, pricer=None):
+    """cfg2 chain for price / greeks / iv_greeks; cfg3 (strata: deep OTM, short expiry, below intrinsic,
+    above maximum, t < 0) for the IV workload.  `pricer` supplies cfg3's clean BSM prices."""
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2, chain_cfg3
+    if workload == "iv" and pricer is not None:
+        return chain_cfg3(n, seed=seed, pricer=pricer)
+    return chain_cfg2(n, seed=seed)
+
+
+# DP instructions (DFMA+DMUL+DADD+DSETP, thread level, divergence included) per contract, from the ncu
+# captures under profiles/ (smsp__inst_executed by opcode x 32 / contracts); used for the fp64 fraction
+DP_INST_PER_CONTRACT = {"greeks": 2664.0, "price": 369.0, "iv": 2129.0, "iv_greeks": 4681.0}
 
 
 class ClockSampler:
@@ -108,8 +116,10 @@ def cpu_baseline(workload, model, n_target_s=2.0):
     O = get_oracle()
     threads = O.max_threads
     n = 1_000_000
-    c = make_chain(workload, n, seed=0)
-    if workload in ("iv", "iv_greeks"):
+    c = make_chain(workload, n, seed=0, pricer=lambda f, S, K, t, r, sg, q: O.price("black_scholes_merton", f, S, K, t, r, sg, q, threads=threads)[0])
+    if workload == "iv":
+        price = c["price"]
+    elif workload == "iv_greeks":
         price, _ = O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
 
     def one():
@@ -145,9 +155,11 @@ def run_reference(args):
     O = get_oracle()
     threads = O.max_threads
     n = 1_000_000  # bounded sample per step
-    c = make_chain(args.workload, n, seed=0)
+    c = make_chain(args.workload, n, seed=0, pricer=lambda f, S, K, t, r, sg, q: O.price("black_scholes_merton", f, S, K, t, r, sg, q, threads=threads)[0])
     price = None
-    if args.workload in ("iv", "iv_greeks"):
+    if args.workload == "iv":
+        price = c["price"]
+    elif args.workload == "iv_greeks":
         price, _ = O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
 
     def step():
@@ -207,15 +219,21 @@ def main():
         bytes_in += 8
 
     # ---- inputs: N_SETS independent seeded chains per rank, resident in HBM ------------------------
+    def gpu_pricer(f, S_, K_, t_, r_, sg_, q_):
+        col = lambda a: (np.ascontiguousarray(a), 1)  # noqa: E731
+        return E.price("black_scholes_merton", f.size, col(f), col(S_), col(K_), col(t_), col(r_), col(q_), col(sg_), ctx=E.get_ctx(local))
+
     sets = []
     for k in range(N_SETS):
-        c = make_chain(wl, n, seed=1000 * rank + k)
+        c = make_chain(wl, n, seed=1000 * rank + k, pricer=gpu_pricer)
         d = {key: torch.from_numpy(np.ascontiguousarray(c[key])).to(dev) for key in ("flag", "S", "K", "t", "r", "sigma", "q")}
         d["host"] = c
         outs = {key: torch.empty(n, dtype=torch.float64, device=dev) for key in ("price", "delta", "gamma", "theta", "rho", "vega", "iv")}
         d["out"] = outs
         d["status"] = torch.empty(n, dtype=torch.uint8, device=dev)
-        if wl in ("iv", "iv_greeks"):
+        if wl == "iv":
+            d["mprice"] = torch.from_numpy(np.ascontiguousarray(c["price"])).to(dev)
+        elif wl == "iv_greeks":
             d["mprice"] = torch.empty(n, dtype=torch.float64, device=dev)
             E.price_dev(model, n, d["flag"], d["S"], d["K"], d["t"], d["r"], d["q"] if bsm else None, d["sigma"], d["mprice"])
         sets.append(d)
@@ -332,8 +350,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                          "note": "kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8(d)); see fp64"},
-            "fp64": {"peak_dp_inst_per_s_nofma": fp64_peak, "peak_dp_inst_per_s_fma": fp64_peak_fma,
-                     "how": "dependent DMUL+DADD (and DFMA) chains, 8 per thread, measured in this run"},
+            "fp64": {"achieved_dp_inst_per_s": value / world * DP_INST_PER_CONTRACT[wl], "peak_dp_inst_per_s_nofma": fp64_peak,
+                     "peak_dp_inst_per_s_fma": fp64_peak_fma, "frac": value / world * DP_INST_PER_CONTRACT[wl] / fp64_peak,
+                     "dp_inst_per_contract": DP_INST_PER_CONTRACT[wl],
+                     "how": "peak: dependent DMUL+DADD (and DFMA) chains, 8 per thread, measured in this run; "
+                            "achieved: contracts/s x DP instructions per contract counted by ncu (profiles/)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, model)

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) price_kernel(long long n, con
                                                              long long *first_zde, long long base) {
     __shared__ pvv::PriceItems<kTileItems> items;
     __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    pvv::tile_sort_init(ts);
     const int tid = threadIdx.x;
     const long long tile_base = (long long)blockIdx.x * kTileItems;
 #pragma unroll 1
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
     constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
     __shared__ pvv::PriceItems<kTileItems> items;
     __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    pvv::tile_sort_init(ts);
     const int tid = threadIdx.x;
     const int c = tid % kGreekContracts;     // contract within the tile
     const int half = tid / kGreekContracts;  // warp-uniform split of the staging work
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
     unsigned status = 0;
     stage_greeks<BSM>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, stencil_need(want), status);
     if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    __syncthreads();  // the sort classifies items staged by other threads (two threads per contract)
     pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(
         items, ts, [&](int item) { note_zde(first_zde, base + (long long)blockIdx.x * kGreekContracts + (item % kGreekContracts)); });
     if (!valid || half != 0) return;
@@ -261,7 +264,8 @@ struct IvShared {
 
 __device__ __forceinline__ double nbc_batch(IvShared &sh, double x, double s, bool active, unsigned &st) {
     const int tid = threadIdx.x;
-    __syncthreads();  // the arrays may still be read by the previous stage
+    // no barrier needed here: outside the sorted evaluation every thread touches only its own slot,
+    // and the previous stage ended with a barrier
     sh.a[0][tid] = active ? x : 0.0;
     sh.a[1][tid] = active ? s : 0.0;  // (0, 0) classifies as R_ZERO and costs nothing
     sh.zde[tid] = 0;
@@ -289,8 +293,7 @@ __device__ __forceinline__ double iv_tile_solve(IvShared &sh, double beta, doubl
     const double b_2 = nbc_batch(sh, x, s_2, active, st);
     // initial guess, contracts regrouped by branch
     const int br = active ? pvv::iv_branch(beta, b_c, b_2) : pvv::IV_DONE;
-    __syncthreads();
-    sh.a[0][tid] = x;
+    sh.a[0][tid] = x;  // own slots only: no barrier needed after the batch's closing one
     sh.a[1][tid] = beta;
     sh.a[2][tid] = b_max;
     sh.a[3][tid] = s_c;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_kernel(long long n, const in
                                                            double *__restrict__ iv, uint8_t *__restrict__ status_out, long long *first_zde,
                                                            long long base) {
     __shared__ IvShared sh;
+    pvv::tile_sort_init(sh.ts);
     const long long i = (long long)blockIdx.x * kIvThreads + threadIdx.x;
     const bool valid = i < n;
     unsigned status = 0;
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
     __shared__ __align__(16) unsigned char raw[sizeof(IvGreeksUnion)];
     IvShared &sh = reinterpret_cast<IvGreeksUnion *>(raw)->iv;
     IvGreeksShared &gs = reinterpret_cast<IvGreeksUnion *>(raw)->g;
+    pvv::tile_sort_init(sh.ts);
     const int tid = threadIdx.x;
     const long long tile0 = (long long)blockIdx.x * kIvThreads;
     const long long i = tile0 + tid;
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
     if (valid) iv[i] = vol;
     __syncthreads();  // the solver's shared arrays are dead from here on
     gs.vol[tid] = vol;
+    pvv::tile_sort_init(gs.ts);
     const unsigned want = (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) | (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
     const unsigned need = stencil_need(want);
 #pragma unroll 1
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
             gs.zf[half][c] = (sst & pvv::ST_ZERO_DIVISION) ? 1 : 0;
             if (half == 0) gs.zf[2][c] = 0;
         }
+        __syncthreads();  // the sort classifies items staged by other threads
         pvv::eval_price_items<kIvThreads, kTileItems / kIvThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kGreekContracts] = 1; });
         if (gvalid && half == 0) finish_greeks(gs.items, c, gi, f, Si, Ki, ti, nullptr, delta, gamma, theta, rho, vega);
         __syncthreads();  // zf[2] written during the evaluation

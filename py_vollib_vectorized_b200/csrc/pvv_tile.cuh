@@ -24,11 +24,19 @@ struct TileSort {
 };
 
 // Counting sort of the tile's T items by key_of(item) in [0, 8).  All NT threads must call it.
+// Contract: ts.cnt[] is zero on entry (tile_sort_init once per kernel, then every sort re-zeroes it
+// on exit), and at least one __syncthreads() separates two sorts' counting phases — the callers'
+// own end-of-stage barrier provides it.  key_of(item) is called for the items j*NT + tid: if those
+// were written by OTHER threads the caller must put a barrier before the sort.  Two barriers per sort.
+template <int NT, int IPT>
+__device__ __forceinline__ void tile_sort_init(TileSort<NT, IPT> &ts) {
+    if (threadIdx.x < 8) ts.cnt[threadIdx.x] = 0;
+    __syncthreads();
+}
+
 template <int NT, int IPT, class KeyOf>
 __device__ __forceinline__ void tile_sort(TileSort<NT, IPT> &ts, KeyOf key_of) {
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 8) ts.cnt[tid] = 0;
-    __syncthreads();
     int key[IPT], pos[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
@@ -52,6 +60,7 @@ __device__ __forceinline__ void tile_sort(TileSort<NT, IPT> &ts, KeyOf key_of) {
         ts.order[start + pos[j]] = (unsigned short)((j * NT + tid) | (key[j] << 12));
     }
     __syncthreads();
+    if (tid < 8) ts.cnt[tid] = 0;  // every thread has read cnt[] before the barrier above
 }
 
 // One work item of the pricing tiles: everything needed to turn b(x, s) into a discounted price.
