@@ -89,7 +89,8 @@ PVV_API int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const do
                       double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream);
 
 /* ---- host-buffer entry points (chunked multi-stream pipeline inside the library) ------------- */
-/* chunk_contracts <= 0 and n_streams <= 0 pick defaults (4 Mi contracts, 3 streams). */
+/* chunk_contracts <= 0 and n_streams <= 0 pick defaults (512 Ki contracts, 3 streams: the measured
+ * optimum on PCIe Gen5, tools/tune_e2e.py). */
 PVV_API int pvv_ctx_create(int device, int64_t chunk_contracts, int n_streams, pvv_ctx **out);
 PVV_API void pvv_ctx_destroy(pvv_ctx *ctx);
 
@@ -110,6 +111,12 @@ PVV_API int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t 
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 PVV_API int64_t pvv_launch_count(void);
+
+/* ---- host ingest helper (no GPU involved) ------------------------------------------------------- */
+/* out[i] = vals[j] where in[i] == keys[j], else 0; returns the number of unmatched elements.  Used by
+ * the Python host to encode an object-dtype flag column ('c'/'p' singletons) in one threaded pass;
+ * replaces the per-element dict lookup of util/data_format.py:10-11. */
+PVV_API int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *keys, const int8_t *vals, int8_t *out, int threads);
 
 /* ---- diagnostics used by the parity tests ----------------------------------------------------- */
 /* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf */

@@ -54,6 +54,8 @@ def _load():
     lib.pvv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp]
     lib.pvv_iv_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp, vp]
     lib.pvv_iv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp] + [vp] * 5 + [vp]
+    lib.pvv_match_u64.restype = i64
+    lib.pvv_match_u64.argtypes = [i64, vp, i32, vp, vp, vp, i32]
     lib.pvv_unary_dev.argtypes = [i32, i64, vp, vp, vp]
     lib.pvv_fp64_probe.argtypes = [i64, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     return lib
@@ -68,6 +70,13 @@ def lib():
 
 def launch_count():
     return int(_lib.pvv_launch_count())
+
+
+def match_u64(addr, n, keys, vals, out):
+    """out[i] = vals[j] where the uint64 at addr + 8 i equals keys[j]; returns the number of misses."""
+    k = np.ascontiguousarray(keys, dtype=np.uint64)
+    v = np.ascontiguousarray(vals, dtype=np.int8)
+    return int(_lib.pvv_match_u64(n, ctypes.c_void_p(addr), k.size, _hp(k), _hp(v), _hp(out), 0))
 
 
 def _check(code):
@@ -117,6 +126,58 @@ def _hp(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
+# ---- pinned host memory (plumbing) ------------------------------------------------------------------
+# A cudaMemcpyAsync from/to PAGEABLE memory is staged by the driver and blocks (measured on the B200
+# box, 10 M contracts, K2: 127 ms pageable vs 12 ms pinned, tools/probe_ingest.py).  So:
+#   * outputs are allocated pinned (torch's caching host allocator makes that free after first use) and
+#     handed to the caller as ordinary numpy arrays — the DMA lands directly in the returned array;
+#   * large pageable input columns are copied once into pinned staging arrays, one thread per column
+#     (numpy's copy releases the GIL), before the pipeline starts.
+_PIN_MIN_ELEMS = 1 << 15
+_pool = None
+
+
+def _pinned_empty(n, dtype):
+    if n >= _PIN_MIN_ELEMS:
+        try:
+            import torch
+            tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.uint8): torch.uint8, np.dtype(np.int8): torch.int8}[np.dtype(dtype)]
+            return torch.empty(n, dtype=tdt, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(n, dtype=dtype)
+
+
+def _is_pinned(a):
+    try:
+        import torch
+        return torch.from_numpy(a).is_pinned()
+    except Exception:
+        return False
+
+
+def _stage(arrays):
+    """arrays: list of contiguous numpy arrays or None.  Returns the list with every large pageable
+    array replaced by a pinned copy."""
+    global _pool
+    todo = [i for i, a in enumerate(arrays) if a is not None and a.size >= _PIN_MIN_ELEMS and not _is_pinned(a)]
+    if not todo:
+        return arrays
+    out = list(arrays)
+    dst = {i: _pinned_empty(arrays[i].size, arrays[i].dtype) for i in todo}
+    if len(todo) == 1 or arrays[todo[0]].nbytes < (4 << 20):
+        for i in todo:
+            np.copyto(dst[i], arrays[i])
+    else:
+        if _pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _pool = ThreadPoolExecutor(max_workers=8)
+        list(_pool.map(lambda i: np.copyto(dst[i], arrays[i]), todo))
+    for i in todo:
+        out[i] = dst[i]
+    return out
+
+
 def _hcol(col):
     """(array|None, stride) -> contiguous float64 host array (kept alive by the caller) and stride."""
     if col is None:
@@ -131,6 +192,15 @@ def _hflag(col):
     return np.ascontiguousarray(a, dtype=np.int8), int(s)
 
 
+def _prepare(flag, cols):
+    """Common front of the host entry points: contiguous typed columns, strides, pinned staging."""
+    f, sf = _hflag(flag)
+    cols = [_hcol(c) for c in cols]
+    staged = _stage([f] + [c[0] for c in cols])
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    return staged[0], staged[1:], stride
+
+
 def _raise_zde(first):
     if first >= 0:
         # numba's error model raises for the whole call (SURVEY.md Appendix B)
@@ -140,13 +210,11 @@ def _raise_zde(first):
 def price(model, n, flag, S, K, t, r, q, sigma, *, ctx=None, out=None, raise_zde=True):
     """Host path of K1.  Columns are (array, stride) pairs; returns a float64 array of n prices."""
     ctx = ctx or get_ctx()
-    f, sf = _hflag(flag)
-    cols = [_hcol(c) for c in (S, K, t, r, q, sigma)]
-    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
-    out = np.empty(n, dtype=np.float64) if out is None else out
+    f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
+    out = _pinned_empty(n, np.float64) if out is None else out
     first = ctypes.c_int64(-1)
     with ctx.lock:
-        _check(_lib.pvv_price_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), _hp(out),
+        _check(_lib.pvv_price_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), _hp(out),
                                    ctypes.byref(first)))
     if raise_zde:
         _raise_zde(first.value)
@@ -159,15 +227,13 @@ GREEK_NAMES = ("delta", "gamma", "theta", "rho", "vega")
 def greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price=False, ctx=None, outs=None, raise_zde=True):
     """Host path of K2.  Returns dict name -> float64 array for the requested outputs."""
     ctx = ctx or get_ctx()
-    f, sf = _hflag(flag)
-    cols = [_hcol(c) for c in (S, K, t, r, q, sigma)]
-    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
     names = (("price",) if with_price else ()) + tuple(want)
-    outs = outs or {k: np.empty(n, dtype=np.float64) for k in names}
+    outs = outs or {k: _pinned_empty(n, np.float64) for k in names}
     first = ctypes.c_int64(-1)
     ptrs = [_hp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
     with ctx.lock:
-        _check(_lib.pvv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), *ptrs,
+        _check(_lib.pvv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), *ptrs,
                                     ctypes.byref(first)))
     if raise_zde:
         _raise_zde(first.value)
@@ -177,14 +243,12 @@ def greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price
 def iv(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, ctx=None, out=None, status=None):
     """Host path of K3.  Returns (iv, status, first_zero_division_index)."""
     ctx = ctx or get_ctx()
-    f, sf = _hflag(flag)
-    cols = [_hcol(c) for c in (price_col, S, K, t, r, q)]
-    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
-    out = np.empty(n, dtype=np.float64) if out is None else out
-    status = np.empty(n, dtype=np.uint8) if status is None else status
+    f, cols, stride = _prepare(flag, (price_col, S, K, t, r, q))
+    out = _pinned_empty(n, np.float64) if out is None else out
+    status = _pinned_empty(n, np.uint8) if status is None else status
     first = ctypes.c_int64(-1)
     with ctx.lock:
-        _check(_lib.pvv_iv_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride), int(bool(mask_errors)),
+        _check(_lib.pvv_iv_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), int(bool(mask_errors)),
                                 _hp(out), _hp(status), ctypes.byref(first)))
     return out, status, first.value
 
@@ -192,15 +256,13 @@ def iv(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, ctx=None, 
 def iv_greeks(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, want=GREEK_NAMES, ctx=None, outs=None, status=None):
     """Host path of K4.  Returns (dict(iv, greeks...), status, first_zero_division_index)."""
     ctx = ctx or get_ctx()
-    f, sf = _hflag(flag)
-    cols = [_hcol(c) for c in (price_col, S, K, t, r, q)]
-    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
-    outs = outs or {k: np.empty(n, dtype=np.float64) for k in ("iv",) + tuple(want)}
-    status = np.empty(n, dtype=np.uint8) if status is None else status
+    f, cols, stride = _prepare(flag, (price_col, S, K, t, r, q))
+    outs = outs or {k: _pinned_empty(n, np.float64) for k in ("iv",) + tuple(want)}
+    status = _pinned_empty(n, np.uint8) if status is None else status
     first = ctypes.c_int64(-1)
     ptrs = [_hp(outs.get(k)) for k in GREEK_NAMES]
     with ctx.lock:
-        _check(_lib.pvv_iv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c[0]) for c in cols], _hp(stride),
+        _check(_lib.pvv_iv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride),
                                        int(bool(mask_errors)), _hp(outs["iv"]), _hp(status), *ptrs, ctypes.byref(first)))
     return outs, status, first.value
 

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <thread>
+#include <vector>
 #include <climits>
 #include <cstdio>
 #include <new>
@@ -712,12 +714,20 @@ int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_str
     if (flag_stride == 0) hf[0] = flag[0];
     PVV_CK(cudaMemcpyAsync((char *)c->scalars + 64, hf, 8, cudaMemcpyHostToDevice, c->stream[0]));
     PVV_CK(cudaStreamSynchronize(c->stream[0]));
-    long long nchunks = (n + c->chunk - 1) / c->chunk;
+    // effective chunk: the ctx's chunk for long columns; for short ones about a quarter of the call so
+    // that H2D, kernel and D2H of neighbouring chunks still overlap (measured: tools/tune_e2e.py)
+    long long chunk = c->chunk;
+    if (n < 4 * chunk) {
+        chunk = ((n + 3) / 4 + 1023) / 1024 * 1024;
+        if (chunk < 65536) chunk = 65536;
+        if (chunk > c->chunk) chunk = c->chunk;
+    }
+    long long nchunks = (n + chunk - 1) / chunk;
     for (long long k = 0; k < nchunks; ++k) {
         const int si = (int)(k % c->nstreams);
         cudaStream_t s = c->stream[si];
-        const long long off = k * c->chunk;
-        const long long m = (n - off < c->chunk) ? (n - off) : c->chunk;
+        const long long off = k * chunk;
+        const long long m = (n - off < chunk) ? (n - off) : chunk;
         SlotView v = view(c, si);
         const double *dev_in[kInCols];
         for (int j = 0; j < n_in; ++j) {
@@ -759,7 +769,7 @@ int pvv_ctx_create(int device, int64_t chunk_contracts, int n_streams, pvv_ctx *
     pvv_ctx *c = new (std::nothrow) pvv_ctx();
     if (!c) return PVV_E_OUT_OF_MEMORY;
     c->device = device;
-    c->chunk = chunk_contracts > 0 ? chunk_contracts : (4ll << 20);
+    c->chunk = chunk_contracts > 0 ? chunk_contracts : (512ll << 10);
     c->nstreams = n_streams > 0 ? (n_streams > 8 ? 8 : n_streams) : 3;
     cudaError_t e = cudaSetDevice(device);
     for (int i = 0; i < c->nstreams && e == cudaSuccess; ++i) {
@@ -853,6 +863,42 @@ int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, c
                                                     theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
                                                     (int64_t *)ctx->first_zde, off, s);
                         });
+}
+
+// Host-side helper of the flag ingest (util/data_format.py): out[i] = vals[j] where in[i] == keys[j],
+// 0 where nothing matches; returns the number of unmatched elements.  The Python side hands over the
+// PyObject* values of an object column and the addresses of the handful of singleton objects a flag
+// cell can be ('c', 'p', 1, -1, ...): one multi-threaded pass over 8 bytes per element replaces the
+// reference's per-element dict lookup (util/data_format.py:10-11, 51 % of its wall time at 1 M rows).
+int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *keys, const int8_t *vals, int8_t *out, int threads) {
+    if (n <= 0) return 0;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads > 16) threads = 16;
+    if (threads < 1 || n < (1 << 16)) threads = 1;
+    std::vector<int64_t> missing((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        int64_t miss = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint64_t v = in[i];
+            int8_t o = 0;
+            for (int k = 0; k < nkeys; ++k)
+                if (v == keys[k]) o = vals[k];
+            out[i] = o;
+            miss += (o == 0);
+        }
+        missing[(size_t)t] = miss;
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (int64_t m : missing) total += m;
+    return total;
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@ Same accepted inputs, same exceptions and warning texts as the reference
   * the below-intrinsic / above-maximum masks come back from the IV kernel as a status byte per
     contract instead of ~10 numpy temporaries (data_format.py:42-72).
 """
+import ctypes
 import warnings
 
 import numpy as np
@@ -35,7 +36,9 @@ def _preprocess_flags(flags, dtype=np.float64):
     if isinstance(flags, str):
         seq = list(flags)  # the reference iterates a bare string character by character
     elif isinstance(flags, (pd.Series, pd.Index)):
-        seq = flags.values
+        if isinstance(flags.dtype, pd.StringDtype):
+            return _encode_string_series(pd.Series(flags))
+        seq = flags.to_numpy()
     elif isinstance(flags, pd.DataFrame):
         seq = list(flags)  # iterating a frame yields its column labels, as in the reference
     else:
@@ -58,6 +61,15 @@ def _preprocess_flags(flags, dtype=np.float64):
         if bad.any():
             raise KeyError(arr[bad][0].item())
         return out
+    if kind == "U" and arr.dtype.itemsize == 4 and arr.flags.c_contiguous:  # '<U1': compare code points
+        cp = arr.view(np.uint32)
+        out = np.zeros(arr.shape, dtype=np.int8)
+        out[(cp == ord('c')) | (cp == ord('1'))] = 1
+        out[cp == ord('p')] = -1
+        bad = out == 0
+        if bad.any():
+            raise KeyError(arr[bad][0].item())
+        return out
     if kind in "US":
         a = arr.astype(str)
         out = np.zeros(a.shape, dtype=np.int8)
@@ -67,11 +79,47 @@ def _preprocess_flags(flags, dtype=np.float64):
         if bad.any():
             raise KeyError(a[bad][0].item())
         return out
-    # object column (the usual pandas string column, possibly mixed): hash-map in C
-    mapped = pd.Series(arr, dtype=object).map(binary_flag)
-    if mapped.isna().any():
-        raise KeyError(arr[np.flatnonzero(mapped.isna().values)[0]])
-    return mapped.values.astype(np.int8)
+    # object column (the usual pandas string column, possibly mixed)
+    return _encode_object_flags(arr)
+
+
+def _singleton_ids():
+    """ids of the objects a flag cell usually IS: CPython keeps one object per one-character Latin-1
+    string (what numpy / pandas / csv readers produce), a second one for the interned literal, and
+    one per small int."""
+    ids = {}
+    for key in ('c', 'p', '1'):
+        ids[id(key)] = binary_flag[key]
+        ids[id(chr(ord(key)))] = binary_flag[key]
+    ids[id(1)] = 1
+    ids[id(-1)] = -1
+    return ids
+
+
+def _encode_object_flags(arr):
+    """Object array -> int8 flags: compare the PyObject* values vectorised (8 bytes per element) and
+    send only the stragglers (e.g. '-1', float 1.0, freshly built strings) through the reference's dict."""
+    from .. import _engine
+    arr = np.ascontiguousarray(arr)
+    n = arr.size
+    ids = _singleton_ids()
+    out = np.empty(n, dtype=np.int8)
+    missing = _engine.match_u64(arr.ctypes.data, n, list(ids.keys()), list(ids.values()), out)
+    if missing:
+        rest = np.flatnonzero(out == 0)
+        out[rest] = [binary_flag[f] for f in arr[rest]]
+    return out
+
+
+def _encode_string_series(s):
+    """pandas string-dtype column (Arrow-backed in pandas 3): vectorised equality, no object array."""
+    out = np.zeros(len(s), dtype=np.int8)
+    for key in ('c', 'p', '1', '-1'):
+        out[(s == key).to_numpy(dtype=bool, na_value=False)] = binary_flag[key]
+    bad = out == 0
+    if bad.any():
+        raise KeyError(s.iloc[int(np.flatnonzero(bad)[0])])
+    return out
 
 
 def _maybe_format_data(data, dtype):
