@@ -119,7 +119,8 @@ PVV_API int64_t pvv_launch_count(void);
 PVV_API int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *keys, const int8_t *vals, int8_t *out, int threads);
 
 /* ---- diagnostics used by the parity tests ----------------------------------------------------- */
-/* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf */
+/* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf,
+ * 6 pow(x, 1/3) */
 PVV_API int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void *stream);
 /* measured FP64 issue rate: runs a dependent DADD/DMUL (fmad off) chain, returns elapsed ms via *ms
  * for `iters` x 2 instructions per thread over `threads` threads */

@@ -460,6 +460,7 @@ __global__ void unary_kernel(int which, long long n, const double *__restrict__ 
         case 2: o = pvv::erfcx_cody(v); break;
         case 3: o = pvv::erfc_cody(v); break;
         case 4: o = pvv::norm_cdf(v); break;
+        case 6: o = pvv::pow_g(v, 1. / 3.); break;
         default: o = pvv::inverse_norm_cdf(v); break;
     }
     y[i] = o;

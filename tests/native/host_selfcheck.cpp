@@ -12,6 +12,8 @@ X double pvvh_erfcx(double x) { return pvv::erfcx_cody(x); }
 X double pvvh_erfc(double x) { return pvv::erfc_cody(x); }
 X double pvvh_norm_cdf(double x) { return pvv::norm_cdf(x); }
 X double pvvh_inverse_norm_cdf(double x) { return pvv::inverse_norm_cdf(x); }
+X double pvvh_pow(double x, double y) { return pvv::pow_g(x, y); }
+X void pvvh_pow_array(long n, const double *x, double y, double *out) { for (long i = 0; i < n; ++i) out[i] = pvv::pow_g(x[i], y); }
 X void pvvh_exp_array(long n, const double *x, double *y) { for (long i = 0; i < n; ++i) y[i] = pvv::exp_g(x[i]); }
 X void pvvh_log_array(long n, const double *x, double *y) { for (long i = 0; i < n; ++i) y[i] = pvv::log_g(x[i]); }
 X double pvvh_const(int which) {

@@ -1,0 +1,99 @@
+"""GPU tier at BASELINE.json's sizes: cfg2 (1 M Black-Scholes chain, price + greeks) and cfg3 (10 M
+BSM implied volatility with strata) against the multi-threaded oracle bit for bit, plus the
+size-independent properties the domain offers (price -> IV -> price round trip, put-call parity,
+launch-shape invariance: one launch == chunked pipeline == device-pointer path)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+GREEKS = ("delta", "gamma", "theta", "rho", "vega")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from py_vollib_vectorized_b200 import _engine
+    return _engine
+
+
+def col(a):
+    return (np.ascontiguousarray(a), 1)
+
+
+def test_cfg2_one_million_price_and_greeks(eng, oracle):
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    n = 1_000_000
+    c = chain_cfg2(n, seed=0)
+    th = oracle.max_threads
+    for model in ("black_scholes", "black_scholes_merton"):
+        q = col(c["q"]) if model == "black_scholes_merton" else None
+        out = eng.greeks(model, n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q, col(c["sigma"]), with_price=True)
+        ref, zde = oracle.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=th)
+        assert zde == -1
+        for k in ("price",) + GREEKS:
+            assert_bit_equal(ref[k], out[k], f"{model} {k}")
+    p = eng.price("black", n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), None, None, col(c["sigma"]))
+    assert_bit_equal(oracle.price("black", c["flag"], c["S"], c["K"], c["t"], 0.0, c["sigma"], threads=th)[0], p, "black")
+    # put-call parity of the undiscounted Black price: C - P = F - K (to rounding of the larger leg)
+    call = eng.price("black", n, (np.ones(1, dtype=np.int8), 0), col(c["S"]), col(c["K"]), col(c["t"]), None, None, col(c["sigma"]))
+    put = eng.price("black", n, (-np.ones(1, dtype=np.int8), 0), col(c["S"]), col(c["K"]), col(c["t"]), None, None, col(c["sigma"]))
+    assert np.abs((call - put) - (c["S"] - c["K"])).max() <= 1e-12 * np.maximum(c["S"], c["K"]).max()
+
+
+def test_cfg3_ten_million_iv_with_strata(eng, oracle):
+    import torch
+    from py_vollib_vectorized_b200.util.chains import chain_cfg3
+    n = 10_000_000
+    th = oracle.max_threads
+
+    def gpu_pricer(f, S, K, t, r, sg, q):
+        return eng.price("black_scholes_merton", f.size, col(f), col(S), col(K), col(t), col(r), col(q), col(sg))
+
+    c = chain_cfg3(n, seed=1, pricer=gpu_pricer)
+    args = (col(c["flag"]), col(c["price"]), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), col(c["q"]))
+    for mask in (True, False):
+        iv, status, zde = eng.iv("black_scholes_merton", n, *args, mask_errors=mask)
+        ref, st_ref, zde_ref = oracle.iv("black_scholes_merton", c["price"], c["S"], c["K"], c["t"], c["r"], c["flag"], c["q"],
+                                         mask_errors=mask, threads=th)
+        assert zde == zde_ref == -1
+        assert (status == st_ref).all()
+        assert_bit_equal(ref, iv, f"10M IV mask={mask}")
+    st = c["strata"]
+    iv_w, status, _ = eng.iv("black_scholes_merton", n, *args, mask_errors=True)
+    assert (status[st["below"]] & 1).all() and np.isnan(iv_w[st["below"]]).all()
+    assert (status[st["above"]] & 2).all() and np.isnan(iv_w[st["above"]]).all()
+    assert np.isnan(iv_w[st["tneg"]]).all() and not (status[st["tneg"]] & 3).any()
+    # round trip: repricing at the solved volatility gives the price back
+    ok = np.isfinite(iv_w) & (iv_w > 0) & ~st["deep"]
+    idx = np.flatnonzero(ok)[::7]
+    rp = eng.price("black_scholes_merton", idx.size, col(c["flag"][idx]), col(c["S"][idx]), col(c["K"][idx]), col(c["t"][idx]),
+                   col(c["r"][idx]), col(c["q"][idx]), col(iv_w[idx]))
+    rel = np.abs(rp - c["price"][idx]) / c["price"][idx]
+    assert np.quantile(rel, 0.999) < 1e-9
+    # launch-shape invariance: device-pointer path (one launch) == host pipeline (chunks)
+    d = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in ("flag", "price", "S", "K", "t", "r", "q")}
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    stt = torch.empty(n, dtype=torch.uint8, device="cuda")
+    eng.iv_dev("black_scholes_merton", n, d["flag"], d["price"], d["S"], d["K"], d["t"], d["r"], d["q"], out, stt)
+    assert_bit_equal(iv_w, out.cpu().numpy(), "dev vs host pipeline")
+    assert (stt.cpu().numpy() == status).all()
+
+
+def test_cfg4_fused_iv_greeks_two_million(eng, oracle):
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    n = 2_000_000
+    c = chain_cfg2(n, seed=2)
+    th = oracle.max_threads
+    price = eng.price("black_scholes", n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), None, col(c["sigma"]))
+    outs, status, zde = eng.iv_greeks("black_scholes", n, col(c["flag"]), col(price), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), None)
+    ref, st_ref, _ = oracle.iv_greeks("black_scholes", price, c["S"], c["K"], c["t"], c["r"], c["flag"], threads=th)
+    assert zde == -1 and (status == st_ref).all()
+    for k in ("iv",) + GREEKS:
+        assert_bit_equal(ref[k], outs[k], f"fused {k}")
+    good = np.isfinite(outs["iv"]) & (outs["iv"] > 0)
+    assert np.quantile(np.abs(outs["iv"][good] - c["sigma"][good]), 0.99) < 1e-6
