@@ -304,33 +304,35 @@ __device__ __forceinline__ double iv_tile_solve(IvShared &sh, double beta, doubl
     sh.a[6][tid] = s_2;
     sh.a[7][tid] = b_2;
     pvv::tile_sort(sh.ts, [&](int) { return br; });
-    {
-        const unsigned e = sh.ts.order[tid];
-        const int item = e & 0xfffu, branch = e >> 12;
-        if (branch != pvv::IV_DONE) {
-            const pvv::IvState g = pvv::iv_initial_guess(branch, sh.a[0][item], sh.a[1][item], sh.a[2][item], sh.a[3][item], sh.a[4][item],
-                                                         sh.a[5][item], sh.a[6][item], sh.a[7][item]);
-            sh.a[0][item] = g.s;
-            sh.a[1][item] = g.s_left;
-            sh.a[2][item] = g.s_right;
-            sh.mode[item] = (unsigned char)g.mode;
-        }
-    }
-    __syncthreads();
+    // From here on thread j works on contract order[j] — the tile stays grouped by solver branch, so
+    // the initial guess AND the two Householder passes (whose formulas differ per branch) run in
+    // branch-uniform warps.  The result returns to the owner thread through shared memory at the end.
+    const unsigned e = sh.ts.order[tid];
+    const int item = e & 0xfffu, branch = e >> 12;
+    const bool active2 = branch != pvv::IV_DONE;
+    const double x2 = sh.a[0][item], beta2 = sh.a[1][item], b_max2 = sh.a[2][item];
     pvv::IvState o;
-    o.s = sh.a[0][tid];
-    o.s_left = sh.a[1][tid];
-    o.s_right = sh.a[2][tid];
-    o.mode = sh.mode[tid];
+    o.s = 0.0;
+    o.s_left = 0.0;
+    o.s_right = 0.0;
+    o.mode = pvv::MODE_MIDDLE;
+    if (active2) o = pvv::iv_initial_guess(branch, x2, beta2, b_max2, sh.a[3][item], sh.a[4][item], sh.a[5][item], sh.a[6][item], sh.a[7][item]);
+    __syncthreads();  // the guess inputs are consumed; a[] becomes the batch arrays again
     double ds = -DBL_MAX;
-    bool running = active;
+    bool running = active2;
+    unsigned st2 = 0;
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
         if (running) running = pvv::iv_iteration_head(it, ds, o);
-        const double b = nbc_batch(sh, x, o.s, running, st);
-        if (running) ds = pvv::iv_iteration_tail(x, beta, b_max, b, o);
+        const double b = nbc_batch(sh, x2, o.s, running, st2);
+        if (running) ds = pvv::iv_iteration_tail(x2, beta2, b_max2, b, o);
     }
-    return active ? o.s : 0.0;
+    // hand the result back: a[2] / mode[] are not used by the batches
+    sh.a[2][item] = active2 ? o.s : 0.0;
+    sh.mode[item] = (unsigned char)(st2 & pvv::ST_ZERO_DIVISION);
+    __syncthreads();
+    if (sh.mode[tid]) st |= pvv::ST_ZERO_DIVISION;
+    return sh.a[2][tid];
 }
 
 template <int MODEL>
