@@ -39,6 +39,9 @@ WORKLOADS = {
            "cfg3: 10M-contract BSM implied volatility with deep-OTM / short-expiry / below-intrinsic strata (kernel K3)"),
     "iv_greeks": ("IV+greeks contracts/s", "black_scholes", 12_500_000, 41, 49,
                   "cfg4: mixed call/put chain, IV then greeks at the solved vol (kernel K4), 12.5M contracts per GPU"),
+    "surface": ("price_dataframe rows/s", "black", 10_000_000, 41, 48,
+                "cfg5 (scaled 10x down in expiries): Black-76 surface grid 2000 strikes x 50 expiries x 100 underlyings via "
+                "price_dataframe(model='black', sigma_col=...), e2e from a pandas frame with a string flag column"),
 }
 N_SETS = 4  # rotating input/output sets so that the working set exceeds the 126 MB L2
 
@@ -55,18 +58,26 @@ def parse():
     return ap.parse_args()
 
 
+def make_surface(n):
+    from py_vollib_vectorized_b200.util.chains import chain_cfg5
+    ne = max(1, n // (2000 * 100))
+    return chain_cfg5(2000, ne, 100)
+
+
 def make_chain(workload, n, seed, pricer=None):
     """cfg2 chain for price / greeks / iv_greeks; cfg3 (strata: deep OTM, short expiry, below intrinsic,
     above maximum, t < 0) for the IV workload.  `pricer` supplies cfg3's clean BSM prices."""
     from py_vollib_vectorized_b200.util.chains import chain_cfg2, chain_cfg3
     if workload == "iv" and pricer is not None:
         return chain_cfg3(n, seed=seed, pricer=pricer)
+    if workload == "surface":
+        return make_surface(n)
     return chain_cfg2(n, seed=seed)
 
 
 # DP instructions (DFMA+DMUL+DADD+DSETP, thread level, divergence included) per contract, from the ncu
 # captures under profiles/ (smsp__inst_executed by opcode x 32 / contracts); used for the fp64 fraction
-DP_INST_PER_CONTRACT = {"greeks": 2664.0, "price": 369.0, "iv": 2129.0, "iv_greeks": 4681.0}
+DP_INST_PER_CONTRACT = {"greeks": 2664.0, "price": 369.0, "iv": 2129.0, "iv_greeks": 4681.0, "surface": 2664.0 + 369.0}
 
 
 class ClockSampler:
@@ -116,6 +127,8 @@ def cpu_baseline(workload, model, n_target_s=2.0):
     O = get_oracle()
     threads = O.max_threads
     n = 1_000_000
+    if workload == "surface":
+        n = 2_000_000
     c = make_chain(workload, n, seed=0, pricer=lambda f, S, K, t, r, sg, q: O.price("black_scholes_merton", f, S, K, t, r, sg, q, threads=threads)[0])
     if workload == "iv":
         price = c["price"]
@@ -123,7 +136,10 @@ def cpu_baseline(workload, model, n_target_s=2.0):
         price, _ = O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
 
     def one():
-        if workload == "greeks":
+        if workload == "surface":
+            O.price("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+            O.greeks("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+        elif workload == "greeks":
             O.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif workload == "price":
             O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
@@ -155,6 +171,8 @@ def run_reference(args):
     O = get_oracle()
     threads = O.max_threads
     n = 1_000_000  # bounded sample per step
+    if args.workload == "surface":
+        n = 2_000_000
     c = make_chain(args.workload, n, seed=0, pricer=lambda f, S, K, t, r, sg, q: O.price("black_scholes_merton", f, S, K, t, r, sg, q, threads=threads)[0])
     price = None
     if args.workload == "iv":
@@ -163,7 +181,10 @@ def run_reference(args):
         price, _ = O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
 
     def step():
-        if args.workload == "greeks":
+        if args.workload == "surface":
+            O.price("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+            O.greeks("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+        elif args.workload == "greeks":
             O.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif args.workload == "price":
             O.price(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
@@ -213,6 +234,8 @@ def main():
     metric, model, n, bytes_in, bytes_out, desc = WORKLOADS[args.workload]
     if args.n:
         n = args.n
+    if args.workload == "surface":
+        n = max(1, n // 200000) * 200000  # whole expiries of the 2000 x 100 grid
     wl = args.workload
     bsm = model == "black_scholes_merton"
     if bsm and wl != "iv":
@@ -242,7 +265,11 @@ def main():
 
     def step_dev(d):
         o = d["out"]
-        if wl == "greeks":
+        if wl == "surface":
+            E.price_dev("black", n, d["flag"], d["S"], d["K"], d["t"], None, None, d["sigma"], o["price"])
+            E.greeks_dev("black", n, d["flag"], d["S"], d["K"], d["t"], d["r"], None, d["sigma"],
+                         {k: o[k] for k in ("delta", "gamma", "theta", "rho", "vega")})
+        elif wl == "greeks":
             E.greeks_dev(model, n, d["flag"], d["S"], d["K"], d["t"], d["r"], q_of(d), d["sigma"],
                          {k: o[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
         elif wl == "price":
@@ -284,7 +311,7 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
     value = world * n * args.steps / (ms * 1e-3)
-    kernel_ms = ms / args.steps  # one kernel launch per step
+    kernel_ms = ms / args.steps  # one kernel launch per step (two for the surface workload)
 
     # ---- end to end: host (pinned) buffers through pvv_*_host, H2D + D2H inside the timed region ----
     h = sets[0]["host"]
@@ -298,8 +325,17 @@ def main():
     col = lambda k: (hin[k], 1)  # noqa: E731
     qh = col("q") if bsm else None
 
+    if wl == "surface":
+        import pandas as pd
+        import py_vollib_vectorized_b200 as pvv
+        frame = pd.DataFrame({"Flag": np.where(h["flag"] > 0, "c", "p"), "F": h["S"], "K": h["K"], "T": h["t"], "R": h["r"], "IV": h["sigma"]})
+
     def step_host():
-        if wl == "greeks":
+        if wl == "surface":
+            res = pvv.price_dataframe(frame, flag_col="Flag", underlying_price_col="F", strike_col="K", annualized_tte_col="T",
+                                      riskfree_rate_col="R", sigma_col="IV", model="black", inplace=False)
+            assert res.shape == (n, 6)
+        elif wl == "greeks":
             E.greeks(model, n, col("flag"), col("S"), col("K"), col("t"), col("r"), qh, col("sigma"), with_price=True, ctx=ctx,
                      outs={k: hout[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
         elif wl == "price":
@@ -310,7 +346,7 @@ def main():
             E.iv_greeks(model, n, col("flag"), col("price"), col("S"), col("K"), col("t"), col("r"), qh, ctx=ctx, status=hstatus,
                         outs={k: hout[k] for k in ("iv", "delta", "gamma", "theta", "rho", "vega")})
 
-    e2e_steps = max(3, min(args.steps, 50))
+    e2e_steps = max(3, min(args.steps, 50 if wl != "surface" else 5))
     for _ in range(3):
         step_host()
     barrier()
@@ -344,7 +380,7 @@ def main():
                        "l2": f"{N_SETS} rotating input/output sets per GPU ({N_SETS * n * (bytes_in + bytes_out) / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"contracts sharded over {world} GPU(s), no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": "contracts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "how": "pvv_*_host C-ABI call on pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline, wall clock"},
+                    "steps": e2e_steps, "how": ("price_dataframe() on a pandas frame (pageable memory, string flag column): flag encode + pinned staging + pipeline + frame assembly, wall clock" if wl == "surface" else "pvv_*_host C-ABI call on pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline, wall clock")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

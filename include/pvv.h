@@ -118,6 +118,10 @@ PVV_API int64_t pvv_launch_count(void);
  * replaces the per-element dict lookup of util/data_format.py:10-11. */
 PVV_API int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *keys, const int8_t *vals, int8_t *out, int threads);
 
+/* out[i] = lut[in[i]] (256-entry table) for flag columns that arrive as one byte per cell; returns the
+ * number of zeros written. */
+PVV_API int64_t pvv_lut_u8(int64_t n, const uint8_t *in, const int8_t *lut, int8_t *out, int threads);
+
 /* ---- diagnostics used by the parity tests ----------------------------------------------------- */
 /* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf,
  * 6 pow(x, 1/3) */

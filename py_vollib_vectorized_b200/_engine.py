@@ -54,6 +54,8 @@ def _load():
     lib.pvv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp]
     lib.pvv_iv_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp, vp]
     lib.pvv_iv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp] + [vp] * 5 + [vp]
+    lib.pvv_lut_u8.restype = i64
+    lib.pvv_lut_u8.argtypes = [i64, vp, vp, vp, i32]
     lib.pvv_match_u64.restype = i64
     lib.pvv_match_u64.argtypes = [i64, vp, i32, vp, vp, vp, i32]
     lib.pvv_unary_dev.argtypes = [i32, i64, vp, vp, vp]
@@ -77,6 +79,11 @@ def match_u64(addr, n, keys, vals, out):
     k = np.ascontiguousarray(keys, dtype=np.uint64)
     v = np.ascontiguousarray(vals, dtype=np.int8)
     return int(_lib.pvv_match_u64(n, ctypes.c_void_p(addr), k.size, _hp(k), _hp(v), _hp(out), 0))
+
+
+def lut_u8(data, lut, out):
+    """out[i] = lut[data[i]] for a uint8 array; returns the number of zeros written."""
+    return int(_lib.pvv_lut_u8(data.size, _hp(data), _hp(lut), _hp(out), 0))
 
 
 def _check(code):
@@ -149,11 +156,27 @@ def _pinned_empty(n, dtype):
 
 
 def _is_pinned(a):
+    if not a.flags.writeable:  # torch.from_numpy refuses read-only views (pandas hands those out); stage them
+        return False
     try:
         import torch
         return torch.from_numpy(a).is_pinned()
     except Exception:
         return False
+
+
+def pin_columns(cols):
+    """(array, stride) columns -> the same columns with every large pageable array replaced by a pinned
+    copy, so that several engine calls on the same inputs (price_dataframe) stage them only once."""
+    arrays = []
+    for c in cols:
+        if c is None:
+            arrays.append(None)
+        else:
+            a = c[0]
+            arrays.append(np.ascontiguousarray(a, dtype=np.int8 if a.dtype == np.int8 else np.float64))
+    staged = _stage(arrays)
+    return [None if c is None else (staged[i], c[1]) for i, c in enumerate(cols)]
 
 
 def _stage(arrays):

@@ -127,8 +127,9 @@ def price_dataframe(df, *, flag_col=None, underlying_price_col=None, strike_col=
     # one broadcast for everything the kernels need
     extra = [x for x in (price, sigma, q) if x is not None]
     c = maybe_format_data_and_broadcast(*inputs, *extra, dtype=dtype)
-    S, K, t, r, flag = c.cols[:5]
-    rest = list(c.cols[5:])
+    cols = _engine.pin_columns(c.cols)  # one pinned staging copy serves every kernel call below
+    S, K, t, r, flag = cols[:5]
+    rest = list(cols[5:])
     price_c = rest.pop(0) if price is not None else None
     sigma_c = rest.pop(0) if sigma is not None else None
     q_c = rest.pop(0) if q is not None else None
@@ -160,4 +161,4 @@ def price_dataframe(df, *, flag_col=None, underlying_price_col=None, strike_col=
         for k, v in results.items():
             df[k] = v
         return None
-    return pd.DataFrame(results, index=df.index)
+    return pd.DataFrame(results, index=df.index, copy=False)

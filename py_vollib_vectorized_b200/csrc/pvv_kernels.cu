@@ -904,4 +904,34 @@ int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *
     return total;
 }
 
+// out[i] = lut[in[i]] over bytes (flag columns that arrive as one byte per cell: Arrow string data of
+// one-character cells); returns the number of zeros written (= unknown flags).  Threaded like pvv_match_u64.
+int64_t pvv_lut_u8(int64_t n, const uint8_t *in, const int8_t *lut, int8_t *out, int threads) {
+    if (n <= 0) return 0;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads > 16) threads = 16;
+    if (threads < 1 || n < (1 << 18)) threads = 1;
+    std::vector<int64_t> missing((size_t)threads, 0);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        int64_t miss = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int8_t o = lut[in[i]];
+            out[i] = o;
+            miss += (o == 0);
+        }
+        missing[(size_t)t] = miss;
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (int64_t m : missing) total += m;
+    return total;
+}
+
 }  // extern "C"

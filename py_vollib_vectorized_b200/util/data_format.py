@@ -112,8 +112,35 @@ def _encode_object_flags(arr):
 
 
 def _encode_string_series(s):
-    """pandas string-dtype column (Arrow-backed in pandas 3): vectorised equality, no object array."""
-    out = np.zeros(len(s), dtype=np.int8)
+    """pandas string-dtype column (Arrow-backed in pandas 3).  Fast path: when every cell is one byte
+    long the Arrow data buffer IS the flag column — compare bytes.  Otherwise vectorised equality."""
+    n = len(s)
+    try:
+        import pyarrow as pa
+        pa_arr = getattr(s.array, "_pa_array", None)
+        if pa_arr is not None and n:
+            if isinstance(pa_arr, pa.ChunkedArray):
+                ca = pa_arr.chunk(0) if pa_arr.num_chunks == 1 else pa_arr.combine_chunks()
+            else:
+                ca = pa_arr
+            if ca.null_count == 0 and (pa.types.is_large_string(ca.type) or pa.types.is_string(ca.type)):
+                bufs = ca.buffers()
+                off_dtype = np.int64 if pa.types.is_large_string(ca.type) else np.int32
+                offsets = np.frombuffer(bufs[1], dtype=off_dtype)[ca.offset:ca.offset + n + 1]
+                # total bytes == n and no cell longer than one byte  =>  every cell is exactly one byte
+                if int(offsets[-1]) - int(offsets[0]) == n and int((offsets[1:] - offsets[:-1]).max()) == 1:
+                    from .. import _engine
+                    data = np.frombuffer(bufs[2], dtype=np.uint8)[int(offsets[0]):int(offsets[-1])]
+                    lut = np.zeros(256, dtype=np.int8)
+                    lut[ord('c')] = lut[ord('1')] = 1
+                    lut[ord('p')] = -1
+                    out = np.empty(n, dtype=np.int8)
+                    if _engine.lut_u8(np.ascontiguousarray(data), lut, out):
+                        raise KeyError(s.iloc[int(np.flatnonzero(out == 0)[0])])
+                    return out
+    except (ImportError, AttributeError, TypeError):
+        pass
+    out = np.zeros(n, dtype=np.int8)
     for key in ('c', 'p', '1', '-1'):
         out[(s == key).to_numpy(dtype=bool, na_value=False)] = binary_flag[key]
     bad = out == 0

@@ -97,3 +97,34 @@ def test_cfg4_fused_iv_greeks_two_million(eng, oracle):
         assert_bit_equal(ref[k], outs[k], f"fused {k}")
     good = np.isfinite(outs["iv"]) & (outs["iv"] > 0)
     assert np.quantile(np.abs(outs["iv"][good] - c["sigma"][good]), 0.99) < 1e-6
+
+
+def test_cfg5_surface_price_dataframe(eng, oracle):
+    """Black-76 surface grid through the public price_dataframe (string flag column, pandas in / out)."""
+    import pandas as pd
+    import py_vollib_vectorized_b200 as pvv
+    from py_vollib_vectorized_b200.util.chains import chain_cfg5
+    c = chain_cfg5(2000, 10, 100)  # 2 M rows, F-major, K fastest
+    n = c["S"].size
+    df = pd.DataFrame({"Flag": np.where(c["flag"] > 0, "c", "p"), "F": c["S"], "K": c["K"], "T": c["t"], "R": c["r"], "IV": c["sigma"]})
+    df.index = np.arange(n)[::-1]  # a non-default index must not disturb positional assignment
+    res = pvv.price_dataframe(df, flag_col="Flag", underlying_price_col="F", strike_col="K", annualized_tte_col="T",
+                              riskfree_rate_col="R", sigma_col="IV", model="black", inplace=False)
+    assert list(res.columns) == ["Price", "delta", "gamma", "theta", "rho", "vega"] and (res.index == df.index).all()
+    th = oracle.max_threads
+    p, _ = oracle.price("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=th)
+    g, _ = oracle.greeks("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=th)
+    assert_bit_equal(p, res["Price"].values, "surface price")
+    for k in GREEKS:
+        assert_bit_equal(g[k], res[k].values, f"surface {k}")
+    # and back: implied volatility + greeks from the prices (K4 through the public API)
+    df["Px"] = res["Price"].values
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        back = pvv.price_dataframe(df, flag_col="Flag", underlying_price_col="F", strike_col="K", annualized_tte_col="T",
+                                   riskfree_rate_col="R", price_col="Px", model="black", inplace=False)
+    ref, st, _ = oracle.iv_greeks("black", res["Price"].values, c["S"], c["K"], c["t"], c["r"], c["flag"], threads=th)
+    assert_bit_equal(ref["iv"], back["IV"].values, "surface IV")
+    for k in GREEKS:
+        assert_bit_equal(ref[k], back[k].values, f"surface IV->{k}")
