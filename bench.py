@@ -39,6 +39,8 @@ WORKLOADS = {
            "cfg3: 10M-contract BSM implied volatility with deep-OTM / short-expiry / below-intrinsic strata (kernel K3)"),
     "iv_greeks": ("IV+greeks contracts/s", "black_scholes", 12_500_000, 41, 49,
                   "cfg4: mixed call/put chain, IV then greeks at the solved vol (kernel K4), 12.5M contracts per GPU"),
+    "analytic": ("price+analytical-greeks contracts/s", "black_scholes", 16_000_000, 41, 48,
+                 "opt-in closed-form greeks (SURVEY 8(f).3): 16M-contract Black-Scholes chain, price + 5 analytical greeks, one HBM-bound pass"),
     "surface": ("price_dataframe rows/s", "black", 10_000_000, 41, 48,
                 "cfg5 (scaled 10x down in expiries): Black-76 surface grid 2000 strikes x 50 expiries x 100 underlyings via "
                 "price_dataframe(model='black', sigma_col=...), e2e from a pandas frame with a string flag column"),
@@ -77,7 +79,7 @@ def make_chain(workload, n, seed, pricer=None):
 
 # DP instructions (DFMA+DMUL+DADD+DSETP, thread level, divergence included) per contract, from the ncu
 # captures under profiles/ (smsp__inst_executed by opcode x 32 / contracts); used for the fp64 fraction
-DP_INST_PER_CONTRACT = {"greeks": 2664.0, "price": 369.0, "iv": 2129.0, "iv_greeks": 4681.0, "surface": 2664.0 + 369.0}
+DP_INST_PER_CONTRACT = {"greeks": 2664.0, "price": 369.0, "iv": 2129.0, "iv_greeks": 4681.0, "surface": 2664.0 + 369.0, "analytic": 230.0}
 
 
 class ClockSampler:
@@ -139,6 +141,8 @@ def cpu_baseline(workload, model, n_target_s=2.0):
         if workload == "surface":
             O.price("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
             O.greeks("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+        elif workload == "analytic":
+            O.analytic_greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif workload == "greeks":
             O.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif workload == "price":
@@ -184,6 +188,8 @@ def run_reference(args):
         if args.workload == "surface":
             O.price("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
             O.greeks("black", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], threads=threads)
+        elif args.workload == "analytic":
+            O.analytic_greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif args.workload == "greeks":
             O.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=threads)
         elif args.workload == "price":
@@ -269,6 +275,9 @@ def main():
             E.price_dev("black", n, d["flag"], d["S"], d["K"], d["t"], None, None, d["sigma"], o["price"])
             E.greeks_dev("black", n, d["flag"], d["S"], d["K"], d["t"], d["r"], None, d["sigma"],
                          {k: o[k] for k in ("delta", "gamma", "theta", "rho", "vega")})
+        elif wl == "analytic":
+            E.analytic_greeks_dev(model, n, d["flag"], d["S"], d["K"], d["t"], d["r"], q_of(d), d["sigma"],
+                                  {k: o[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
         elif wl == "greeks":
             E.greeks_dev(model, n, d["flag"], d["S"], d["K"], d["t"], d["r"], q_of(d), d["sigma"],
                          {k: o[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
@@ -335,6 +344,9 @@ def main():
             res = pvv.price_dataframe(frame, flag_col="Flag", underlying_price_col="F", strike_col="K", annualized_tte_col="T",
                                       riskfree_rate_col="R", sigma_col="IV", model="black", inplace=False)
             assert res.shape == (n, 6)
+        elif wl == "analytic":
+            E.analytic_greeks(model, n, col("flag"), col("S"), col("K"), col("t"), col("r"), qh, col("sigma"), with_price=True, ctx=ctx,
+                              outs={k: hout[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
         elif wl == "greeks":
             E.greeks(model, n, col("flag"), col("S"), col("K"), col("t"), col("r"), qh, col("sigma"), with_price=True, ctx=ctx,
                      outs={k: hout[k] for k in ("price", "delta", "gamma", "theta", "rho", "vega")})
@@ -385,7 +397,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                         "note": "kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8(d)); see fp64"},
+                         "note": ("closed-form kernel: HBM is the binding roofline" if wl == "analytic" else "kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8(d)); see fp64")},
             "fp64": {"achieved_dp_inst_per_s": value / world * DP_INST_PER_CONTRACT[wl], "peak_dp_inst_per_s_nofma": fp64_peak,
                      "peak_dp_inst_per_s_fma": fp64_peak_fma, "frac": value / world * DP_INST_PER_CONTRACT[wl] / fp64_peak,
                      "dp_inst_per_contract": DP_INST_PER_CONTRACT[wl],

@@ -88,6 +88,19 @@ PVV_API int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const do
                       const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
                       double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream);
 
+/* Opt-in closed-form greeks (py_vollib `greeks.analytical` conventions: theta per calendar day, vega
+ * and rho per point).  model 1 or 2.  Any output may be NULL.  No reference
+ * counterpart in py_vollib_vectorized (its greeks are finite differences): tolerance 1e-12 against the
+ * closed-form oracle, 6 decimals against the reference's regression table. */
+PVV_API int pvv_analytic_greeks_dev(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t,
+                                    const double *r, const double *q, const double *sigma, const int64_t stride[7], double *price,
+                                    double *delta, double *gamma, double *theta, double *rho, double *vega, void *stream);
+PVV_API int pvv_analytic_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *S, const double *K,
+                                     const double *t, const double *r, const double *q, const double *sigma, const int64_t stride[7],
+                                     double *price, double *delta, double *gamma, double *theta, double *rho, double *vega);
+/* internal: bumps the launch counter from other translation units of the library */
+PVV_API void pvv_note_launch(void);
+
 /* ---- host-buffer entry points (chunked multi-stream pipeline inside the library) ------------- */
 /* chunk_contracts <= 0 and n_streams <= 0 pick defaults (512 Ki contracts, 3 streams: the measured
  * optimum on PCIe Gen5, tools/tune_e2e.py). */

@@ -58,6 +58,8 @@ class Oracle:
         L.pvv_oracle_price.argtypes = [i32, i64] + [vp] * 9 + [i32]
         L.pvv_oracle_greeks.restype = i64
         L.pvv_oracle_greeks.argtypes = [i32, i64] + [vp] * 14 + [i32]
+        L.pvv_oracle_analytic_greeks.restype = None
+        L.pvv_oracle_analytic_greeks.argtypes = [i32, i64] + [vp] * 14 + [i32]
         L.pvv_oracle_iv.restype = i64
         L.pvv_oracle_iv.argtypes = [i32, i64] + [vp] * 8 + [i32] + [vp] * 3 + [i32]
         L.pvv_oracle_iv_greeks.restype = i64
@@ -102,6 +104,18 @@ class Oracle:
         if not with_price:
             outs.pop("price")
         return outs, int(zde)
+
+    def analytic_greeks(self, model, flag, S, K, t, r, sigma, q=None, threads=1):
+        """Closed-form price and greeks (py_vollib greeks.analytical conventions)."""
+        m = _MODELS[model]
+        n = self._n(flag, S, K, t, r, sigma, q)
+        f, sf = _flag(flag, n)
+        cols = [_col(c if c is not None else 0.0, n) for c in (S, K, t, r, q, sigma)]
+        stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+        names = ["price", "delta", "gamma", "theta", "rho", "vega"]
+        outs = {k: np.empty(n, dtype=np.float64) for k in names}
+        self.lib.pvv_oracle_analytic_greeks(m, n, _p(f), *[_p(c[0]) for c in cols], _p(stride), *[_p(outs[k]) for k in names], threads)
+        return outs
 
     def iv(self, model, price, S, K, t, r, flag, q=None, mask_errors=True, threads=1, want_branch=False):
         """Returns (iv, status, zde_index[, branch])."""

@@ -54,6 +54,8 @@ def _load():
     lib.pvv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp]
     lib.pvv_iv_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp, vp]
     lib.pvv_iv_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp, i32, vp, vp] + [vp] * 5 + [vp]
+    lib.pvv_analytic_greeks_dev.argtypes = [i32, i64] + [vp] * 7 + [vp] + [vp] * 6 + [vp]
+    lib.pvv_analytic_greeks_host.argtypes = [vp, i32, i64] + [vp] * 7 + [vp] + [vp] * 6
     lib.pvv_lut_u8.restype = i64
     lib.pvv_lut_u8.argtypes = [i64, vp, vp, vp, i32]
     lib.pvv_match_u64.restype = i64
@@ -260,6 +262,28 @@ def greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price
                                     ctypes.byref(first)))
     if raise_zde:
         _raise_zde(first.value)
+    return outs
+
+
+def analytic_greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price=False, ctx=None, outs=None):
+    """Host path of the opt-in closed-form greeks kernel (pvv_analytic_greeks_host)."""
+    ctx = ctx or get_ctx()
+    f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
+    names = (("price",) if with_price else ()) + tuple(want)
+    outs = outs or {k: _pinned_empty(n, np.float64) for k in names}
+    ptrs = [_hp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
+    with ctx.lock:
+        _check(_lib.pvv_analytic_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), *ptrs))
+    return outs
+
+
+def analytic_greeks_dev(model, n, flag, S, K, t, r, q, sigma, outs):
+    torch = _torch()
+    f, sf = _dcol(flag, n, torch.int8)
+    cols = [_dcol(c, n, torch.float64) for c in (S, K, t, r, q, sigma)]
+    stride = np.array([sf] + [c[1] for c in cols], dtype=np.int64)
+    ptrs = [_dp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
+    _check(_lib.pvv_analytic_greeks_dev(MODELS[model], n, _dp(f), *[_dp(c[0]) for c in cols], _hp(stride), *ptrs, _stream_ptr()))
     return outs
 
 

@@ -29,10 +29,16 @@ _Q_ERROR = "Must pass a `q` to black scholes merton model (annualized continuous
 _GREEKS = ("delta", "gamma", "theta", "rho", "vega")
 
 
-def get_all_greeks(flag, S, K, t, r, sigma, q=None, *, model="black_scholes", return_as="dataframe", dtype=np.float64):
+def get_all_greeks(flag, S, K, t, r, sigma, q=None, *, model="black_scholes", return_as="dataframe", dtype=np.float64,
+                   method="numerical"):
     """
-    All five finite-difference greeks of each contract, as specified by `model`
+    All five greeks of each contract, as specified by `model`
     ("black" uses the Black-Scholes stencil, exactly as the reference does).
+
+    `method="numerical"` (default) reproduces the reference's finite differences bit for bit.
+    `method="analytical"` (an extension; models black_scholes / black_scholes_merton) returns the
+    closed-form greeks in py_vollib's `greeks.analytical` conventions — theta per calendar day, vega
+    and rho per point — from a single HBM-bound pass.
 
     >>> get_all_greeks(['c', 'p'], 95, [100, 90], .2, .2, .2, model='black_scholes', return_as='dict')
     {'delta': array([ 0.46750566, -0.1364465 ]),
@@ -41,17 +47,24 @@ def get_all_greeks(flag, S, K, t, r, sigma, q=None, *, model="black_scholes", re
      'rho': array([ 0.0830349 , -0.02715114]),
      'vega': array([0.16892575, 0.0928379 ])}
     """
+    if method not in ("numerical", "analytical"):
+        raise ValueError("`method` must be 'numerical' or 'analytical'")
+    compute = _engine.greeks
+    if method == "analytical":
+        if model == "black":
+            raise ValueError("Analytical greeks are available for `black_scholes` and `black_scholes_merton`")
+        compute = _engine.analytic_greeks
     flag = _preprocess_flags(flag, dtype=dtype)
     c = maybe_format_data_and_broadcast(S, K, t, r, sigma, flag, dtype=dtype)
     if model in ("black", "black_scholes"):
         S, K, t, r, sigma, flag = c
-        greeks = _engine.greeks(model, c.n, flag, S, K, t, r, None, sigma)
+        greeks = compute(model, c.n, flag, S, K, t, r, None, sigma)
     elif model == "black_scholes_merton":
         if q is None:
             raise ValueError(_Q_ERROR)
         c = maybe_format_data_and_broadcast(*c.cols, q, dtype=dtype)
         S, K, t, r, sigma, flag, q = c
-        greeks = _engine.greeks(model, c.n, flag, S, K, t, r, q, sigma)
+        greeks = compute(model, c.n, flag, S, K, t, r, q, sigma)
     else:
         raise ValueError(_MODEL_ERROR)
     greeks = {k: greeks[k] for k in _GREEKS}

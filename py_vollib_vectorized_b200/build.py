@@ -14,16 +14,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpvv.so")
-SOURCES = [os.path.join(CSRC, "pvv_kernels.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "pvv_math.cuh"), os.path.join(CSRC, "glibc_tables.cuh"),
+# (source, extra flags): the parity kernels are compiled WITHOUT fmad, the opt-in analytical kernel with
+UNITS = [(os.path.join(CSRC, "pvv_kernels.cu"), ["-fmad=false"]),
+         (os.path.join(CSRC, "pvv_analytic.cu"), ["-fmad=true"])]
+SOURCES = [u[0] for u in UNITS]
+DEPS = SOURCES + [os.path.join(CSRC, "pvv_math.cuh"), os.path.join(CSRC, "pvv_tile.cuh"), os.path.join(CSRC, "glibc_tables.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "pvv.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
-    "--shared", "-cudart", "shared",
 ]
 
 
@@ -44,16 +45,24 @@ def needs_build():
 def build_extension(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    env = dict(os.environ)
     # the image's default CC wrapper lacks some specs; the system g++ is the host compiler
-    if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libpvv.so")
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+
+    def run(cmd):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building libpvv.so")
+
+    for src, extra in UNITS:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        run([_nvcc()] + ccbin + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+        objs.append(obj)
+    run([_nvcc()] + ccbin + ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared", "-o", LIB] + objs)
     return LIB
 
 

@@ -530,6 +530,7 @@ const char *pvv_error_string(int code) {
 }
 
 int64_t pvv_launch_count(void) { return g_launches.load(); }
+void pvv_note_launch(void) { g_launches++; }
 
 static int launch_price(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
                         const double *q, const double *sigma, const int64_t stride[7], double *price, int64_t *first_zde, long long base,
@@ -865,6 +866,23 @@ int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, c
                                                     v.status, delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr,
                                                     theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
                                                     (int64_t *)ctx->first_zde, off, s);
+                        });
+}
+
+int pvv_analytic_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t,
+                             const double *r, const double *q, const double *sigma, const int64_t stride[7], double *price, double *delta,
+                             double *gamma, double *theta, double *rho, double *vega) {
+    if (!ctx || n < 0 || (model != 1 && model != 2) || (model == 2 && !q)) return PVV_E_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    const double *in[7] = {nullptr, S, K, t, r, (model == 2) ? q : nullptr, sigma};
+    const long long ist[7] = {0, stride[1], stride[2], stride[3], stride[4], stride[5], stride[6]};
+    double *out[6] = {price, delta, gamma, theta, rho, vega};
+    int64_t unused = -1;
+    return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 6, out, nullptr, &unused,
+                        [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long, cudaStream_t s) {
+                            return pvv_analytic_greeks_dev(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, price ? v.out[0] : nullptr,
+                                                           delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr, theta ? v.out[3] : nullptr,
+                                                           rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr, s);
                         });
 }
 

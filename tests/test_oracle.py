@@ -144,3 +144,21 @@ def test_threads_do_not_change_bits(oracle, golden):
     b, _ = oracle.greeks("black_scholes_merton", g["flag"], g["S"], g["K"], g["t"], g["r"], g["sigma"], g["q"], threads=4)
     for k in a:
         assert_bit_equal(a[k], b[k])
+
+
+def test_closed_form_greeks_oracle_is_pinned_by_the_reference_table(oracle, golden):
+    """The checker of the opt-in analytical mode: py_vollib greeks.analytical conventions, pinned by the
+    analytical columns of the reference's own regression table (6 significant digits)."""
+    g = golden("cfg1_json")
+    n = g["S"].size
+    for fl, D, G, T, V, R, P in ((1, "CD", "CG", "CT", "CV", "CR", "bs_call"), (-1, "PD", "PG", "PT", "PV", "PR", "bs_put")):
+        a = oracle.analytic_greeks("black_scholes", np.full(n, fl, np.int8), g["S"], g["K"], g["t"], g["R"], g["v"])
+        assert_array_almost_equal(a["delta"], g[D])
+        assert_array_almost_equal(a["gamma"], g[G])
+        assert_array_almost_equal(a["theta"] * 365, g[T], 4)
+        assert_array_almost_equal(a["vega"], g[V] * .01, 5)
+        assert_array_almost_equal(a["rho"], g[R] * .01, 5)
+        assert_array_almost_equal(a["price"], g[P], 5)
+        b = oracle.analytic_greeks("black_scholes_merton", np.full(n, fl, np.int8), g["S"], g["K"], g["t"], g["R"], g["v"], np.zeros(n))
+        for k in a:
+            assert np.array_equal(a[k], b[k])
