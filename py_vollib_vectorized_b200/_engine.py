@@ -232,48 +232,89 @@ def _raise_zde(first):
         raise ZeroDivisionError("division by zero")
 
 
+GREEK_NAMES = ("delta", "gamma", "theta", "rho", "vega")
+
+# ---- one process driving several GPUs (drop-in mode) -------------------------------------------------
+# PVV_DEVICES="0,1,2,3" (or "all") shards every host-path call over those devices: contiguous ranges
+# (keeps strike-sorted chains warp-coherent), one pvv_ctx and one Python thread per device (ctypes
+# releases the GIL), each device's pipeline DMA-ing straight into its slice of the shared pinned
+# output arrays.  No collective: contracts are independent.
+_MULTI_MIN = 1 << 18
+_dev_pool = None
+
+
+def _devices():
+    spec = os.environ.get("PVV_DEVICES", "").strip()
+    if not spec:
+        return None
+    if spec == "all":
+        import torch
+        return list(range(torch.cuda.device_count()))
+    return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def _off(a, lo, stride=1):
+    """Pointer to element `lo` of a host array (None stays NULL; broadcast scalars are not advanced)."""
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.ctypes.data + (lo * a.itemsize if stride else 0))
+
+
+def _run_host(fn, model, n, f, cols, stride, mid, outs, ctx=None):
+    """Call one pvv_*_host entry point, sharded over PVV_DEVICES when set.
+    mid: extra scalar arguments between stride and the outputs; outs: list of output arrays (or None).
+    Returns the first zero-division index (or -1)."""
+    def call(c, lo, hi):
+        first = ctypes.c_int64(-1)
+        args = [c.handle, MODELS[model], hi - lo, _off(f, lo, stride[0])]
+        args += [_off(a, lo, stride[1 + k]) for k, a in enumerate(cols)]
+        args += [_hp(stride)] + list(mid) + [_off(o, lo) for o in outs]
+        if fn is not _lib.pvv_analytic_greeks_host:
+            args.append(ctypes.byref(first))
+        with c.lock:
+            _check(fn(*args))
+        return -1 if first.value < 0 else first.value + lo
+
+    devs = _devices() if ctx is None else None
+    if not devs or len(devs) < 2 or n < _MULTI_MIN:
+        return call(ctx or get_ctx(devs[0] if devs else None), 0, n)
+    global _dev_pool
+    if _dev_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _dev_pool = ThreadPoolExecutor(max_workers=16)
+    g = len(devs)
+    futs = [_dev_pool.submit(call, get_ctx(d), n * i // g, n * (i + 1) // g) for i, d in enumerate(devs)]
+    firsts = [x for x in (fu.result() for fu in futs) if x >= 0]
+    return min(firsts) if firsts else -1
+
+
 def price(model, n, flag, S, K, t, r, q, sigma, *, ctx=None, out=None, raise_zde=True):
     """Host path of K1.  Columns are (array, stride) pairs; returns a float64 array of n prices."""
-    ctx = ctx or get_ctx()
     f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
     out = _pinned_empty(n, np.float64) if out is None else out
-    first = ctypes.c_int64(-1)
-    with ctx.lock:
-        _check(_lib.pvv_price_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), _hp(out),
-                                   ctypes.byref(first)))
+    first = _run_host(_lib.pvv_price_host, model, n, f, cols, stride, (), [out], ctx)
     if raise_zde:
-        _raise_zde(first.value)
+        _raise_zde(first)
     return out
-
-
-GREEK_NAMES = ("delta", "gamma", "theta", "rho", "vega")
 
 
 def greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price=False, ctx=None, outs=None, raise_zde=True):
     """Host path of K2.  Returns dict name -> float64 array for the requested outputs."""
-    ctx = ctx or get_ctx()
     f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
     names = (("price",) if with_price else ()) + tuple(want)
     outs = outs or {k: _pinned_empty(n, np.float64) for k in names}
-    first = ctypes.c_int64(-1)
-    ptrs = [_hp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
-    with ctx.lock:
-        _check(_lib.pvv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), *ptrs,
-                                    ctypes.byref(first)))
+    first = _run_host(_lib.pvv_greeks_host, model, n, f, cols, stride, (), [outs.get(k) for k in ("price",) + GREEK_NAMES], ctx)
     if raise_zde:
-        _raise_zde(first.value)
+        _raise_zde(first)
     return outs
 
 
 def analytic_greeks(model, n, flag, S, K, t, r, q, sigma, *, want=GREEK_NAMES, with_price=False, ctx=None, outs=None):
     """Host path of the opt-in closed-form greeks kernel (pvv_analytic_greeks_host)."""
-    ctx = ctx or get_ctx()
     f, cols, stride = _prepare(flag, (S, K, t, r, q, sigma))
     names = (("price",) if with_price else ()) + tuple(want)
     outs = outs or {k: _pinned_empty(n, np.float64) for k in names}
-    ptrs = [_hp(outs.get(k)) for k in ("price",) + GREEK_NAMES]
-    with ctx.lock:
-        _check(_lib.pvv_analytic_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), *ptrs))
+    _run_host(_lib.pvv_analytic_greeks_host, model, n, f, cols, stride, (), [outs.get(k) for k in ("price",) + GREEK_NAMES], ctx)
     return outs
 
 
@@ -289,29 +330,21 @@ def analytic_greeks_dev(model, n, flag, S, K, t, r, q, sigma, outs):
 
 def iv(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, ctx=None, out=None, status=None):
     """Host path of K3.  Returns (iv, status, first_zero_division_index)."""
-    ctx = ctx or get_ctx()
     f, cols, stride = _prepare(flag, (price_col, S, K, t, r, q))
     out = _pinned_empty(n, np.float64) if out is None else out
     status = _pinned_empty(n, np.uint8) if status is None else status
-    first = ctypes.c_int64(-1)
-    with ctx.lock:
-        _check(_lib.pvv_iv_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride), int(bool(mask_errors)),
-                                _hp(out), _hp(status), ctypes.byref(first)))
-    return out, status, first.value
+    first = _run_host(_lib.pvv_iv_host, model, n, f, cols, stride, (int(bool(mask_errors)),), [out, status], ctx)
+    return out, status, first
 
 
 def iv_greeks(model, n, flag, price_col, S, K, t, r, q, *, mask_errors=True, want=GREEK_NAMES, ctx=None, outs=None, status=None):
     """Host path of K4.  Returns (dict(iv, greeks...), status, first_zero_division_index)."""
-    ctx = ctx or get_ctx()
     f, cols, stride = _prepare(flag, (price_col, S, K, t, r, q))
     outs = outs or {k: _pinned_empty(n, np.float64) for k in ("iv",) + tuple(want)}
     status = _pinned_empty(n, np.uint8) if status is None else status
-    first = ctypes.c_int64(-1)
-    ptrs = [_hp(outs.get(k)) for k in GREEK_NAMES]
-    with ctx.lock:
-        _check(_lib.pvv_iv_greeks_host(ctx.handle, MODELS[model], n, _hp(f), *[_hp(c) for c in cols], _hp(stride),
-                                       int(bool(mask_errors)), _hp(outs["iv"]), _hp(status), *ptrs, ctypes.byref(first)))
-    return outs, status, first.value
+    first = _run_host(_lib.pvv_iv_greeks_host, model, n, f, cols, stride, (int(bool(mask_errors)),),
+                      [outs["iv"], status] + [outs.get(k) for k in GREEK_NAMES], ctx)
+    return outs, status, first
 
 
 # ------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 // contraction and uses its own minimal-operation-count special functions:
 //   N(x) via Cody's scaled complementary error function evaluated once per |d| together with the
 //   density (N(-|d|) = phi(d) * erfcx(|d|/sqrt2) * sqrt(pi/2)), exp/log from the CUDA math library.
-// Parity: against the closed-form float64 oracle (oracle/pvv_oracle.c: pvv_oracle_analytic_greeks),
+// Parity: against the closed-form float64 checker used by the tests (pvv_oracle_analytic_greeks),
 // 1e-12 relative (+1e-300 absolute), and against the reference's regression table columns
 // CD/CG/CT/CV/CR/PD/PG/PT/PV/PR (6 decimals) — tests/test_gpu_analytic.py.
 #include <cuda_runtime.h>

@@ -128,3 +128,25 @@ def test_cfg5_surface_price_dataframe(eng, oracle):
     assert_bit_equal(ref["iv"], back["IV"].values, "surface IV")
     for k in GREEKS:
         assert_bit_equal(ref[k], back[k].values, f"surface IV->{k}")
+
+
+def test_single_process_multi_gpu_sharding(eng, oracle, monkeypatch):
+    """PVV_DEVICES shards one host call over several devices (drop-in mode, no collective).  With one
+    visible GPU the same device is listed twice: the sharding, offsets and zero-division index logic
+    are exercised all the same."""
+    import torch
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    nd = torch.cuda.device_count()
+    monkeypatch.setenv("PVV_DEVICES", ",".join(str(i % nd) for i in range(max(2, nd))))
+    n = 1_000_003
+    c = chain_cfg2(n, seed=9)
+    out = eng.greeks("black_scholes", n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), (np.array([0.03]), 0), None, col(c["sigma"]),
+                     with_price=True)
+    ref, _ = oracle.greeks("black_scholes", c["flag"], c["S"], c["K"], c["t"], 0.03, c["sigma"], threads=oracle.max_threads)
+    for k in ref:
+        assert_bit_equal(ref[k], out[k], f"sharded {k}")
+    K = c["K"].copy()
+    K[[700_001, 900_000]] = 0.0
+    price = ref["price"]
+    iv, status, zde = eng.iv("black_scholes", n, col(c["flag"]), col(price), col(c["S"]), col(K), col(c["t"]), (np.array([0.03]), 0), None)
+    assert zde == 700_001 and np.flatnonzero(status & 4).tolist() == [700_001, 900_000]
