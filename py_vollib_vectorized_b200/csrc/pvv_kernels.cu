@@ -31,7 +31,6 @@ struct Strides {
     int s[7];
 };
 
-constexpr int kBlock = 128;
 
 __device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
     if (first_zde) atomicMin(first_zde, i);
@@ -495,7 +494,6 @@ __global__ void fp64_probe_kernel(int iters, double *out) {
     if (s == 123.456) out[0] = s;
 }
 
-inline int grid_for(long long n) { return (int)((n + kBlock - 1) / kBlock); }
 inline int grid_tiles(long long n, int per_cta) { return (int)((n + per_cta - 1) / per_cta); }
 
 inline bool fill_strides(const int64_t *stride, Strides &out) {
