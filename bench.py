@@ -102,12 +102,20 @@ class ClockSampler:
         for line in self.p.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: [(label, t0, t1), ...] in order of preference; the first one that contains samples wins
+        (a timed region shorter than the 50 ms sampling period has none: the next window is under load too)."""
         if not self.p:
             return None
         time.sleep(0.06)
         self.p.terminate()
-        rows = [ln.split(", ") for ts, ln in self.lines if t0 <= ts <= t1 + 0.06] or [ln.split(", ") for ts, ln in self.lines[-3:]]
+        rows, label = [], None
+        for label, t0, t1 in windows:
+            rows = [ln.split(", ") for ts, ln in self.lines if t0 <= ts <= t1 + 0.06]
+            if rows:
+                break
+        if not rows:
+            rows, label = [ln.split(", ") for ts, ln in self.lines[-3:]], "last samples"
         sm, mx, reasons = [], 0.0, set()
         for r in rows:
             try:
@@ -120,7 +128,7 @@ class ClockSampler:
                 pass
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": label}
 
 
 def cpu_baseline(workload, model, n_target_s=2.0):
@@ -314,7 +322,6 @@ def main():
     t_wall1 = time.perf_counter()
     launches = E.launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_wall0, t_wall1)
     if world > 1:
         tm = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -368,6 +375,7 @@ def main():
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_s = t1 - t0
+    clocks = sampler.stop([("device-resident timed region", t_wall0, t_wall1), ("end-to-end timed region", t0, t1)])
     if world > 1:
         tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
