@@ -79,7 +79,7 @@ def make_chain(workload, n, seed, pricer=None):
 
 # DP instructions (DFMA+DMUL+DADD+DSETP, thread level, divergence included) per contract, from the ncu
 # captures under profiles/ (smsp__inst_executed by opcode x 32 / contracts); used for the fp64 fraction
-DP_INST_PER_CONTRACT = {"greeks": 2672.0, "price": 370.0, "iv": 1807.0, "iv_greeks": 4378.0, "surface": 2664.0 + 369.0, "analytic": 230.0}
+DP_INST_PER_CONTRACT = {"greeks": 2620.0, "price": 364.0, "iv": 1789.0, "iv_greeks": 4308.0, "surface": 2620.0 + 364.0, "analytic": 267.0}
 
 
 class ClockSampler:
