@@ -82,6 +82,12 @@ def make_chain(workload, n, seed, pricer=None):
 DP_INST_PER_CONTRACT = {"greeks": 2620.0, "price": 364.0, "iv": 1789.0, "iv_greeks": 4308.0, "surface": 2620.0 + 364.0, "analytic": 267.0}
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the ncu --set full
+# captures under profiles/r01_final_ncu_full_summary.txt; below the algorithmic bytes because the outputs of
+# a launch are still resident in the 126 MB L2 when the kernel ends
+TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 47.2, "price": 41.1, "iv": 54.4, "iv_greeks": 72.7, "analytic": 76.8, "surface": 47.2 + 41.1}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -404,7 +410,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                         "traffic": TRAFFIC_BYTES_PER_CONTRACT[wl] * n, "traffic_unit": "bytes per launch (ncu dram read+write, scaled by contracts)",
+                         "algorithmic_bytes": n * (bytes_in + bytes_out), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                          "note": ("closed-form kernel: HBM is the binding roofline" if wl == "analytic" else "kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8(d)); see fp64")},
             "fp64": {"achieved_dp_inst_per_s": value / world * DP_INST_PER_CONTRACT[wl], "peak_dp_inst_per_s_nofma": fp64_peak,
                      "peak_dp_inst_per_s_fma": fp64_peak_fma, "frac": value / world * DP_INST_PER_CONTRACT[wl] / fp64_peak,
