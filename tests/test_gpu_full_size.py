@@ -150,3 +150,32 @@ def test_single_process_multi_gpu_sharding(eng, oracle, monkeypatch):
     price = ref["price"]
     iv, status, zde = eng.iv("black_scholes", n, col(c["flag"]), col(price), col(c["S"]), col(K), col(c["t"]), (np.array([0.03]), 0), None)
     assert zde == 700_001 and np.flatnonzero(status & 4).tolist() == [700_001, 900_000]
+
+
+def test_repeated_ragged_launches_are_deterministic(eng, oracle):
+    """compute-sanitizer is not available on the pool, so shared-memory hazards in the tiled kernels (the
+    sorts reuse their counters and arrays with a minimum of barriers) are hunted the blunt way: many
+    launches of ragged sizes — partial tiles, single contracts, tile-size multiples — every output
+    compared bit for bit with the oracle."""
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2, chain_wide
+    rng = np.random.default_rng(2024)
+    th = oracle.max_threads
+    sizes = [1, 2, 31, 127, 128, 129, 511, 512, 513, 1023, 1024, 1025, 4097] + [int(x) for x in rng.integers(1000, 300000, 12)]
+    for rep, n in enumerate(sizes):
+        c = (chain_cfg2 if rep % 2 == 0 else chain_wide)(n, seed=100 + rep)
+        for model in ("black_scholes", "black_scholes_merton"):
+            q = col(c["q"]) if model == "black_scholes_merton" else None
+            out = eng.greeks(model, n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q, col(c["sigma"]), with_price=True)
+            ref, _ = oracle.greeks(model, c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"], threads=th)
+            for k in ref:
+                assert_bit_equal(ref[k], out[k], f"n={n} {model} {k}")
+            p = eng.price(model, n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q, col(c["sigma"]))
+            assert_bit_equal(ref["price"], p, f"n={n} {model} price kernel")
+            outs, status, zde = eng.iv_greeks(model, n, col(c["flag"]), col(p), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q)
+            ref2, st2, _ = oracle.iv_greeks(model, p, c["S"], c["K"], c["t"], c["r"], c["flag"], c["q"], threads=th)
+            assert (status == st2).all() and zde == -1, n
+            for k in ref2:
+                assert_bit_equal(ref2[k], outs[k], f"n={n} {model} fused {k}")
+            iv, status, _ = eng.iv(model, n, col(c["flag"]), col(p), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q, mask_errors=False)
+            ref3, st3, _ = oracle.iv(model, p, c["S"], c["K"], c["t"], c["r"], c["flag"], c["q"], mask_errors=False, threads=th)
+            assert_bit_equal(ref3, iv, f"n={n} {model} iv")

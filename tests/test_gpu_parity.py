@@ -71,7 +71,7 @@ def test_device_pow_is_the_host_libm(eng):
     import torch
     rng = np.random.default_rng(13)
     x = np.concatenate([np.exp(rng.uniform(-700, 10, 200000)), rng.uniform(0, 1, 200000), rng.uniform(0.9, 1.1, 50000),
-                        1 - np.exp(rng.uniform(-40, -1, 50000)), [1.0, 0.5, 1e-300, 2.0]])
+                        1 - np.exp(rng.uniform(-40, -1, 50000)), np.exp(rng.uniform(-745, -708, 20000)), [1.0, 0.5, 1e-300, 2.0, 5e-324, 1e-310]])
     y = eng.unary_dev("cbrt_pow", torch.from_numpy(x).cuda()).cpu().numpy()
     ref = np.array([math.pow(v, 1. / 3.) for v in x])
     assert_bit_equal(ref, y, "pow(x, 1/3)")
