@@ -271,9 +271,9 @@ __device__ __forceinline__ double nbc_batch(IvShared &sh, double x, double s, bo
     sh.a[0][tid] = active ? x : 0.0;
     sh.a[1][tid] = active ? s : 0.0;  // (0, 0) classifies as R_ZERO and costs nothing
     sh.zde[tid] = 0;
-    pvv::tile_sort(sh.ts, [&](int item) { return pvv::nbc_classify(sh.a[0][item], sh.a[1][item]); });
+    pvv::tile_sort(sh.ts, [&](int item) { return pvv::nbc_sort_key(sh.a[0][item], sh.a[1][item]); });
     const unsigned e = sh.ts.order[tid];
-    const int item = e & 0xfffu, region = e >> 12;
+    const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
     unsigned st2 = 0;
     const double b = pvv::nbc_eval(region, sh.a[0][item], sh.a[1][item], st2);
     sh.a[0][item] = b;

@@ -14,23 +14,24 @@
 
 namespace pvv {
 
-// order[] entries: low 12 bits item id (tile size <= 4096), high bits the sort key
+// order[] entries: low 12 bits item id (tile size <= 4096), high 4 bits the sort key
+constexpr int kSortKeys = 16;
 template <int NT, int IPT>
 struct TileSort {
     static constexpr int T = NT * IPT;
     static_assert(T <= 4096, "item id must fit 12 bits");
     unsigned short order[T];
-    int cnt[8];
+    int cnt[kSortKeys];
 };
 
-// Counting sort of the tile's T items by key_of(item) in [0, 8).  All NT threads must call it.
+// Counting sort of the tile's T items by key_of(item) in [0, 16).  All NT threads must call it.
 // Contract: ts.cnt[] is zero on entry (tile_sort_init once per kernel, then every sort re-zeroes it
 // on exit), and at least one __syncthreads() separates two sorts' counting phases — the callers'
 // own end-of-stage barrier provides it.  key_of(item) is called for the items j*NT + tid: if those
 // were written by OTHER threads the caller must put a barrier before the sort.  Two barriers per sort.
 template <int NT, int IPT>
 __device__ __forceinline__ void tile_sort_init(TileSort<NT, IPT> &ts) {
-    if (threadIdx.x < 8) ts.cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kSortKeys) ts.cnt[threadIdx.x] = 0;
     __syncthreads();
 }
 
@@ -49,18 +50,22 @@ __device__ __forceinline__ void tile_sort(TileSort<NT, IPT> &ts, KeyOf key_of) {
         pos[j] = base + __popc(peers & ((1u << lane) - 1u));
     }
     __syncthreads();
-    int c[8];
+    // exclusive prefix of the 16 counters, redundantly in every warp: lane k holds the start of key k
+    const int c = (lane < kSortKeys) ? ts.cnt[lane] : 0;
+    int incl = c;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) c[k] = ts.cnt[k];
+    for (int d = 1; d < kSortKeys; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int excl = incl - c;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        int start = 0;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) start += (k < key[j]) ? c[k] : 0;
+        const int start = __shfl_sync(0xffffffffu, excl, key[j]);
         ts.order[start + pos[j]] = (unsigned short)((j * NT + tid) | (key[j] << 12));
     }
     __syncthreads();
-    if (tid < 8) ts.cnt[tid] = 0;  // every thread has read cnt[] before the barrier above
+    if (tid < kSortKeys) ts.cnt[tid] = 0;  // every thread has read cnt[] before the barrier above
 }
 
 // One work item of the pricing tiles: everything needed to turn b(x, s) into a discounted price.
@@ -106,12 +111,12 @@ __device__ __forceinline__ void stage_null_item(PriceItems<T> &it, int item) {
 // `on_zde(item)` is called for every item whose evaluation divided by zero (numba would raise).
 template <int NT, int IPT, bool DEFLATE, class OnZde>
 __device__ __forceinline__ void eval_price_items(PriceItems<NT * IPT> &it, TileSort<NT, IPT> &ts, OnZde on_zde) {
-    tile_sort(ts, [&](int item) { return nbc_classify(it.x[item], it.s[item]); });
+    tile_sort(ts, [&](int item) { return nbc_sort_key(it.x[item], it.s[item]); });
     const int tid = threadIdx.x;
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = ts.order[j * NT + tid];
-        const int item = e & 0xfffu, region = e >> 12;
+        const int item = e & 0xfffu, region = key_region(e >> 12);
         unsigned st = 0;
         const double nb = nbc_eval(region, it.x[item], it.s[item], st);
         const double tv = it.scale[item] * nb;
