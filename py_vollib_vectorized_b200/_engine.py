@@ -18,7 +18,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpvv.so")
+# PVV_LIB: development hook — load an A/B build of the engine (build.py --variant) instead of the in-tree one
+LIB_PATH = os.environ.get("PVV_LIB") or os.path.join(_HERE, "libpvv.so")
 
 MODELS = {"black": 0, "black_scholes": 1, "black_scholes_merton": 2}
 

@@ -42,14 +42,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_extension(force=False, verbose=False):
-    if not force and not needs_build():
+def build_extension(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: A/B builds for kernel experiments -> build/libpvv_<variant>.so (loaded with PVV_LIB=...)."""
+    if variant is None and not force and not needs_build():
         return LIB
     # the image's default CC wrapper lacks some specs; the system g++ is the host compiler
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build") if variant is None else os.path.join(HERE, "build", variant)
     os.makedirs(objdir, exist_ok=True)
     objs = []
+    lib = LIB if variant is None else os.path.join(HERE, "build", f"libpvv_{variant}.so")
+    defs = [f"-D{d}" for d in defines]
 
     def run(cmd):
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -60,11 +63,14 @@ def build_extension(force=False, verbose=False):
 
     for src, extra in UNITS:
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        run([_nvcc()] + ccbin + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+        run([_nvcc()] + ccbin + NVCC_FLAGS + extra + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
         objs.append(obj)
-    run([_nvcc()] + ccbin + ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared", "-o", LIB] + objs)
-    return LIB
+    run([_nvcc()] + ccbin + ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "shared", "-o", lib] + objs)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_extension(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    # python build.py [--force] [--verbose] [--variant NAME -DFOO -DBAR=1 ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build_extension(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var,
+                          defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

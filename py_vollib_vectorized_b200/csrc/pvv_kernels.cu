@@ -42,18 +42,27 @@ __device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
 // coalesced).  P1 stages each contract's (x, s, sqrt(F)sqrt(K), intrinsic, deflater) in shared
 // memory, P2 evaluates b(x, s) in region-sorted order (pvv_tile.cuh), P3 stores the prices.
 constexpr int kTileThreads = 256;
+constexpr int kTileCtasPerSm = 1024 / kTileThreads;
 constexpr int kItemsPerThread = 4;
 constexpr int kTileItems = kTileThreads * kItemsPerThread;
 constexpr int kGreekContracts = kTileItems / 8;  // contracts per CTA of the greeks kernel: 8 stencil points each
 
+// shared memory of K1 / K2 (dynamic: above 48 KB for 512-thread tiles)
+struct PriceTileShared {
+    pvv::PriceItems<kTileItems> items;
+    pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+};
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+
 template <int MODEL>
-__global__ void __launch_bounds__(kTileThreads, 4) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                              const double *__restrict__ K, const double *__restrict__ t,
                                                              const double *__restrict__ r, const double *__restrict__ q,
                                                              const double *__restrict__ sigma, Strides st, double *__restrict__ price,
                                                              long long *first_zde, long long base) {
-    __shared__ pvv::PriceItems<kTileItems> items;
-    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    PriceTileShared &psh = *reinterpret_cast<PriceTileShared *>(dyn_smem);
+    pvv::PriceItems<kTileItems> &items = psh.items;
+    pvv::TileSort<kTileThreads, kItemsPerThread> &ts = psh.ts;
     pvv::tile_sort_init(ts);
     const int tid = threadIdx.x;
     const long long tile_base = (long long)blockIdx.x * kTileItems;
@@ -114,9 +123,10 @@ __device__ __forceinline__ unsigned stencil_need(unsigned want) {
 }
 
 // P1 for contract slot c of the tile, done by thread `half` (0: points 0,1,2,6,7; 1: points 3,4,5).
-template <bool BSM>
-__device__ __forceinline__ void stage_greeks(pvv::PriceItems<kTileItems> &items, int c, int half, bool valid, double f, double Si, double Ki,
+template <bool BSM, int T>
+__device__ __forceinline__ void stage_greeks(pvv::PriceItems<T> &items, int c, int half, bool valid, double f, double Si, double Ki,
                                              double ti, double ri, double sg, double qi, unsigned need, unsigned &status) {
+    constexpr int kGreekContracts = T / 8;  // contracts of this tile (shadows the K2 constant: K4 uses larger sub-tiles)
     const double dS = .01;
     if (!valid) {
 #pragma unroll
@@ -186,9 +196,11 @@ __device__ __forceinline__ void stage_greeks(pvv::PriceItems<kTileItems> &items,
 }
 
 // P3: the difference quotients of _numerical_greeks.py from the eight finished prices of slot c.
-__device__ __forceinline__ void finish_greeks(const pvv::PriceItems<kTileItems> &items, int c, long long i, double f, double Si, double Ki,
+template <int T>
+__device__ __forceinline__ void finish_greeks(const pvv::PriceItems<T> &items, int c, long long i, double f, double Si, double Ki,
                                               double ti, double *price, double *delta, double *gamma, double *theta, double *rho,
                                               double *vega) {
+    constexpr int kGreekContracts = T / 8;
     const double dS = .01;
     double p[8];
 #pragma unroll
@@ -207,7 +219,7 @@ __device__ __forceinline__ void finish_greeks(const pvv::PriceItems<kTileItems> 
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                                  const double *__restrict__ K, const double *__restrict__ t,
                                                                  const double *__restrict__ r, const double *__restrict__ q,
                                                                  const double *__restrict__ sigma, Strides st, double *__restrict__ price,
@@ -215,8 +227,9 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
                                                                  double *__restrict__ theta, double *__restrict__ rho,
                                                                  double *__restrict__ vega, long long *first_zde, long long base) {
     constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
-    __shared__ pvv::PriceItems<kTileItems> items;
-    __shared__ pvv::TileSort<kTileThreads, kItemsPerThread> ts;
+    PriceTileShared &psh = *reinterpret_cast<PriceTileShared *>(dyn_smem);
+    pvv::PriceItems<kTileItems> &items = psh.items;
+    pvv::TileSort<kTileThreads, kItemsPerThread> &ts = psh.ts;
     pvv::tile_sort_init(ts);
     const int tid = threadIdx.x;
     const int c = tid % kGreekContracts;     // contract within the tile
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) greeks_kernel(long long n, co
         if (BSM) qi = q[i * st.s[5]];
     }
     unsigned status = 0;
-    stage_greeks<BSM>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, stencil_need(want), status);
+    stage_greeks<BSM, kTileItems>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, stencil_need(want), status);
     if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     __syncthreads();  // the sort classifies items staged by other threads (two threads per contract)
     pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(
@@ -367,13 +380,17 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_kernel(long long n, const in
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
 // One CTA = 512 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2 runs the K2
-// tile machinery four times, 128 contracts (1024 stencil items) at a time, over the same shared
-// memory.  The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
+// tile machinery twice, 256 contracts (2048 stencil items, 84 KB of dynamic shared memory) at a time, over
+// the same shared memory: all 512 threads stage (two per contract) and each evaluates 4 sorted items.
+// (1024-item sub-tiles, where half the threads idle during staging: 1.87 -> 2.14 G contracts/s.)
+// The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
+constexpr int kIvgItems = 2048;                 // stencil items per sub-tile of K4 (4 per thread)
+constexpr int kIvgContracts = kIvgItems / 8;    // 256 contracts per sub-tile: every thread stages one half of a contract
 struct IvGreeksShared {
-    pvv::PriceItems<kTileItems> items;
-    pvv::TileSort<kIvThreads, kTileItems / kIvThreads> ts;
+    pvv::PriceItems<kIvgItems> items;
+    pvv::TileSort<kIvThreads, kIvgItems / kIvThreads> ts;
     double vol[kIvThreads];
-    unsigned char zf[3][kGreekContracts];  // zero-division flags of a sub-tile: staging half 0 / half 1 / evaluation
+    unsigned char zf[3][kIvgContracts];  // zero-division flags of a sub-tile: staging half 0 / half 1 / evaluation
 };
 union IvGreeksUnion {
     IvShared iv;
@@ -390,9 +407,8 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
                                                                   double *__restrict__ theta, double *__restrict__ rho,
                                                                   double *__restrict__ vega, long long *first_zde, long long base) {
     constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
-    __shared__ __align__(16) unsigned char raw[sizeof(IvGreeksUnion)];
-    IvShared &sh = reinterpret_cast<IvGreeksUnion *>(raw)->iv;
-    IvGreeksShared &gs = reinterpret_cast<IvGreeksUnion *>(raw)->g;
+    IvShared &sh = reinterpret_cast<IvGreeksUnion *>(dyn_smem)->iv;
+    IvGreeksShared &gs = reinterpret_cast<IvGreeksUnion *>(dyn_smem)->g;
     pvv::tile_sort_init(sh.ts);
     const int tid = threadIdx.x;
     const long long tile0 = (long long)blockIdx.x * kIvThreads;
@@ -418,11 +434,11 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
     const unsigned want = (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) | (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
     const unsigned need = stencil_need(want);
 #pragma unroll 1
-    for (int sub = 0; sub < kIvThreads / kGreekContracts; ++sub) {
+    for (int sub = 0; sub < kIvThreads / kIvgContracts; ++sub) {
         __syncthreads();
-        const int c = tid % kGreekContracts, half = tid / kGreekContracts;  // threads >= 256 only help in P2
-        const long long gi = tile0 + sub * kGreekContracts + c;
-        const bool gvalid = gi < n && half < 2;
+        const int c = tid % kIvgContracts, half = tid / kIvgContracts;
+        const long long gi = tile0 + sub * kIvgContracts + c;
+        const bool gvalid = gi < n;
         double Si = 0, Ki = 0, ti = 0, f = 1, ri = 0, qi = 0, sg = 0;
         if (gvalid) {
             f = (double)flag[gi * st.s[0]];
@@ -431,19 +447,19 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
             ti = t[gi * st.s[4]];
             ri = r[gi * st.s[5]];
             if (BSM) qi = q[gi * st.s[6]];
-            sg = gs.vol[sub * kGreekContracts + c];
+            sg = gs.vol[sub * kIvgContracts + c];
         }
-        if (half < 2) {
+        {
             unsigned sst = 0;
-            stage_greeks<BSM>(gs.items, c, half, gvalid, f, Si, Ki, ti, ri, sg, qi, need, sst);
+            stage_greeks<BSM, kIvgItems>(gs.items, c, half, gvalid, f, Si, Ki, ti, ri, sg, qi, need, sst);
             gs.zf[half][c] = (sst & pvv::ST_ZERO_DIVISION) ? 1 : 0;
             if (half == 0) gs.zf[2][c] = 0;
         }
         __syncthreads();  // the sort classifies items staged by other threads
-        pvv::eval_price_items<kIvThreads, kTileItems / kIvThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kGreekContracts] = 1; });
+        pvv::eval_price_items<kIvThreads, kIvgItems / kIvThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kIvgContracts] = 1; });
         if (gvalid && half == 0) finish_greeks(gs.items, c, gi, f, Si, Ki, ti, nullptr, delta, gamma, theta, rho, vega);
         __syncthreads();  // zf[2] written during the evaluation
-        if (tid / kGreekContracts == sub && (gs.zf[0][c] | gs.zf[1][c] | gs.zf[2][c])) status |= pvv::ST_ZERO_DIVISION;  // owner thread
+        if (tid / kIvgContracts == sub && (gs.zf[0][c] | gs.zf[1][c] | gs.zf[2][c])) status |= pvv::ST_ZERO_DIVISION;  // owner thread
     }
     if (!valid) return;
     if (status_out) status_out[i] = (uint8_t)status;
@@ -497,6 +513,12 @@ __global__ void fp64_probe_kernel(int iters, double *out) {
 
 inline int grid_tiles(long long n, int per_cta) { return (int)((n + per_cta - 1) / per_cta); }
 
+// dynamic shared memory above the 48 KB default needs the opt-in once per kernel (and per device: cheap, so every launch)
+template <class Kern>
+inline void allow_smem(Kern k, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 inline bool fill_strides(const int64_t *stride, Strides &out) {
     for (int i = 0; i < 7; ++i) {
         if (stride[i] != 0 && stride[i] != 1) return false;
@@ -540,9 +562,9 @@ static int launch_price(int model, int64_t n, const int8_t *flag, const double *
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 0) price_kernel<0><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
-    else if (model == 1) price_kernel<1><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
-    else price_kernel<2><<<grid_tiles(n, kTileItems), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base);
+    if (model == 0) { allow_smem(price_kernel<0>, sizeof(PriceTileShared)); price_kernel<0><<<grid_tiles(n, kTileItems), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base); }
+    else if (model == 1) { allow_smem(price_kernel<1>, sizeof(PriceTileShared)); price_kernel<1><<<grid_tiles(n, kTileItems), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base); }
+    else { allow_smem(price_kernel<2>, sizeof(PriceTileShared)); price_kernel<2><<<grid_tiles(n, kTileItems), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, fz, base); }
     g_launches++;
     return launch_status();
 }
@@ -556,8 +578,8 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 2) greeks_kernel<2><<<grid_tiles(n, kGreekContracts), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
-    else greeks_kernel<1><<<grid_tiles(n, kGreekContracts), kTileThreads, 0, s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base);
+    if (model == 2) { allow_smem(greeks_kernel<2>, sizeof(PriceTileShared)); greeks_kernel<2><<<grid_tiles(n, kGreekContracts), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base); }
+    else { allow_smem(greeks_kernel<1>, sizeof(PriceTileShared)); greeks_kernel<1><<<grid_tiles(n, kGreekContracts), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base); }
     g_launches++;
     return launch_status();
 }
@@ -589,11 +611,11 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
-        iv_greeks_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        { allow_smem(iv_greeks_kernel<0>, sizeof(IvGreeksUnion)); iv_greeks_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     else if (model == 1)
-        iv_greeks_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        { allow_smem(iv_greeks_kernel<1>, sizeof(IvGreeksUnion)); iv_greeks_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     else
-        iv_greeks_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base);
+        { allow_smem(iv_greeks_kernel<2>, sizeof(IvGreeksUnion)); iv_greeks_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     g_launches++;
     return launch_status();
 }
