@@ -259,184 +259,260 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
 }
 
 // ---- K3 / K4: implied volatility ("Let's be rational"), staged over a CTA tile ------------------
-// 512 contracts per CTA, one per thread; the solver state lives in registers.  The solver is run as
-// a sequence of stages for the whole tile; wherever the reference's control flow would diverge,
-// the work is regrouped through shared memory so that warps stay uniform:
-//   B1  b_c = b(x, s_c)              region-sorted batch (pvv_tile.cuh)
-//   B2  b_2 = b(x, s_l or s_h)       region-sorted batch
+// A CTA of NT threads owns C = NT * IPT contracts.  The solver is run as a sequence of stages for the
+// whole tile; the per-contract state (8 doubles) lives in SHARED memory between the stages, and
+// wherever the reference's control flow would diverge the work is regrouped so that warps stay uniform:
+//   B1  b_c = b(x, s_c)              key-sorted batch over all C contracts (pvv_tile.cuh)
+//   B2  b_2 = b(x, s_l or s_h)       key-sorted batch
 //   G   initial guess                contracts sorted by solver branch (lowest / lower-middle /
-//                                    upper-middle / highest), state passed through shared memory
-//   B3, B4  b(x, s) of the two Householder(3) passes, region-sorted batches
-// Per-lane arithmetic is exactly pvv::normalised_iv (pvv_math.cuh), so results are unchanged.
-constexpr int kIvThreads = 512;
-
-struct IvShared {
-    double a[8][kIvThreads];  // batch: a[0] = x -> b, a[1] = s;  guess stage: 8 inputs -> 3 outputs
-    unsigned char zde[kIvThreads];
-    unsigned char mode[kIvThreads];
-    pvv::TileSort<kIvThreads, 1> ts;
+//                                    upper-middle / highest); that order is kept to the end
+//   B3, B4  b(x, s) of the two Householder(3) passes, key-sorted batches
+// Per-contract arithmetic is exactly pvv::normalised_iv (pvv_math.cuh), so results are unchanged.
+// Why IPT > 1: the size of the sorted population decides how uniform the warps are, and with one item
+// per thread a warp that drew an expensive region cannot be balanced.  Measured (10 M BSM contracts,
+// G solves/s): registers-resident state, 512 x 1: 4.30, 1024 x 1: 4.45; shared-memory state,
+// 512 x 2: 4.36, 512 x 3: 5.33, 1024 x 3: 5.49, 768 x 4: 5.19, 384 x 4: 4.98, 512 x 6 (one CTA per SM): 4.42.
+template <int NT, int IPT>
+struct IvTile {
+    static constexpr int C = NT * IPT;
+    double x[C], beta[C], b_max[C];
+    double q[5][C];             // until the guess: s_c, b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, ds, b
+    unsigned char run[C];       // the contract takes part in the current batch
+    unsigned char mode[C];      // iteration objective (MODE_*)
+    unsigned char zde[C];       // a batch evaluation divided by zero
+    unsigned char stat[C];      // status bits of the front
+    pvv::TileSort<NT, IPT> ts;  // order of the b(x, s) batches
+    pvv::TileSort<NT, IPT> tg;  // order by solver branch: fixed from the initial guess to the end
 };
 
-__device__ __forceinline__ double nbc_batch(IvShared &sh, double x, double s, bool active, unsigned &st) {
+// b(x[item], sarr[item]) -> out[item] for every running contract of the tile, in key-sorted order.
+// Entered with all writes to x / sarr / run visible (barrier by the caller); ends with a barrier.
+template <int NT, int IPT>
+__device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, const double *sarr, double *out) {
     const int tid = threadIdx.x;
-    // no barrier needed here: outside the sorted evaluation every thread touches only its own slot,
-    // and the previous stage ended with a barrier
-    sh.a[0][tid] = active ? x : 0.0;
-    sh.a[1][tid] = active ? s : 0.0;  // (0, 0) classifies as R_ZERO and costs nothing
-    sh.zde[tid] = 0;
-    pvv::tile_sort(sh.ts, [&](int item) { return pvv::nbc_sort_key(sh.a[0][item], sh.a[1][item]); });
-    const unsigned e = sh.ts.order[tid];
-    const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
-    unsigned st2 = 0;
-    const double b = pvv::nbc_eval(region, sh.a[0][item], sh.a[1][item], st2);
-    sh.a[0][item] = b;
-    if (st2) sh.zde[item] = 1;
+    pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], sarr[c]) : (int)pvv::K_ZERO; });
+#pragma unroll 1
+    for (int j = 0; j < IPT; ++j) {
+        const unsigned e = sh.ts.order[j * NT + tid];
+        const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
+        unsigned st2 = 0;
+        out[item] = pvv::nbc_eval(region, sh.x[item], sarr[item], st2);
+        if (st2) sh.zde[item] = 1;
+    }
     __syncthreads();
-    if (sh.zde[tid]) st |= pvv::ST_ZERO_DIVISION;
-    return sh.a[0][tid];
 }
 
-// The solver for one tile.  `active` = beta > 0 (else the reference returns 0 without solving).
-__device__ __forceinline__ double iv_tile_solve(IvShared &sh, double beta, double x, bool valid, unsigned &st) {
+// Everything between the front and sigma = s / sqrt(t).  Entered with x, beta, run, zde = 0 filled in
+// natural order by the owner threads (contract c = j * NT + tid); leaves s in q[0] (0 where the
+// reference returns 0 without solving), zde flags in zde[]; ends with a barrier.
+template <int NT, int IPT>
+__device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     const int tid = threadIdx.x;
-    const bool active = valid && !(beta <= 0);
-    const double b_max = pvv::exp_g(0.5 * x);
-    const double s_c = sqrt(fabs(2 * x));
-    const double b_c = nbc_batch(sh, x, s_c, active, st);
-    const double v_c = pvv::normalised_vega(x, s_c);
-    const double s_2 = pvv::iv_second_node(beta, b_max, s_c, b_c, v_c);
-    const double b_2 = nbc_batch(sh, x, s_2, active, st);
-    // initial guess, contracts regrouped by branch
-    const int br = active ? pvv::iv_branch(beta, b_c, b_2) : pvv::IV_DONE;
-    sh.a[0][tid] = x;  // own slots only: no barrier needed after the batch's closing one
-    sh.a[1][tid] = beta;
-    sh.a[2][tid] = b_max;
-    sh.a[3][tid] = s_c;
-    sh.a[4][tid] = b_c;
-    sh.a[5][tid] = v_c;
-    sh.a[6][tid] = s_2;
-    sh.a[7][tid] = b_2;
-    pvv::tile_sort(sh.ts, [&](int) { return br; });
-    // From here on thread j works on contract order[j] — the tile stays grouped by solver branch, so
-    // the initial guess AND the two Householder passes (whose formulas differ per branch) run in
-    // branch-uniform warps.  The result returns to the owner thread through shared memory at the end.
-    const unsigned e = sh.ts.order[tid];
-    const int item = e & 0xfffu, branch = e >> 12;
-    const bool active2 = branch != pvv::IV_DONE;
-    const double x2 = sh.a[0][item], beta2 = sh.a[1][item], b_max2 = sh.a[2][item];
-    pvv::IvState o;
-    o.s = 0.0;
-    o.s_left = 0.0;
-    o.s_right = 0.0;
-    o.mode = pvv::MODE_MIDDLE;
-    if (active2) o = pvv::iv_initial_guess(branch, x2, beta2, b_max2, sh.a[3][item], sh.a[4][item], sh.a[5][item], sh.a[6][item], sh.a[7][item]);
-    __syncthreads();  // the guess inputs are consumed; a[] becomes the batch arrays again
-    double ds = -DBL_MAX;
-    bool running = active2;
-    unsigned st2 = 0;
+    double *s_c = sh.q[0], *b_c = sh.q[1], *v_c = sh.q[2], *s_2 = sh.q[3], *b_2 = sh.q[4];
+#pragma unroll 1
+    for (int j = 0; j < IPT; ++j) {
+        const int c = j * NT + tid;
+        if (!sh.run[c]) continue;
+        const double x = sh.x[c];
+        sh.b_max[c] = pvv::exp_g(0.5 * x);
+        s_c[c] = sqrt(fabs(2 * x));
+    }
+    iv_tile_batch(sh, s_c, b_c);  // own slots only so far: no barrier needed before the sort
+#pragma unroll 1
+    for (int j = 0; j < IPT; ++j) {
+        const int c = j * NT + tid;
+        if (!sh.run[c]) continue;
+        const double x = sh.x[c], sc = s_c[c];
+        const double vc = pvv::normalised_vega(x, sc);
+        v_c[c] = vc;
+        s_2[c] = pvv::iv_second_node(sh.beta[c], sh.b_max[c], sc, b_c[c], vc);
+    }
+    iv_tile_batch(sh, s_2, b_2);
+    // initial guess, contracts regrouped by branch.  From here on thread (j, tid) works on contract
+    // tg.order[j * NT + tid]: the tile stays grouped by solver branch through the Householder passes.
+    pvv::tile_sort(sh.tg, [&](int c) { return sh.run[c] ? pvv::iv_branch(sh.beta[c], b_c[c], b_2[c]) : (int)pvv::IV_DONE; });
+    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *dsa = sh.q[3], *b = sh.q[4];
+#pragma unroll 1
+    for (int j = 0; j < IPT; ++j) {
+        const unsigned e = sh.tg.order[j * NT + tid];
+        const int item = e & 0xfffu, branch = e >> 12;
+        pvv::IvState o;
+        o.s = 0.0;
+        o.s_left = 0.0;
+        o.s_right = 0.0;
+        o.mode = pvv::MODE_MIDDLE;
+        bool running = branch != pvv::IV_DONE;
+        if (running) {
+            o = pvv::iv_initial_guess(branch, sh.x[item], sh.beta[item], sh.b_max[item], s_c[item], b_c[item], v_c[item], s_2[item], b_2[item]);
+            running = pvv::iv_iteration_head(0, -DBL_MAX, o);
+        }
+        s[item] = o.s;  // the item's inputs are consumed: its slots become the iteration state
+        s_left[item] = o.s_left;
+        s_right[item] = o.s_right;
+        dsa[item] = -DBL_MAX;
+        sh.mode[item] = (unsigned char)o.mode;
+        sh.run[item] = running;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        if (running) running = pvv::iv_iteration_head(it, ds, o);
-        const double b = nbc_batch(sh, x2, o.s, running, st2);
-        if (running) ds = pvv::iv_iteration_tail(x2, beta2, b_max2, b, o);
+        iv_tile_batch(sh, s, b);
+#pragma unroll 1
+        for (int j = 0; j < IPT; ++j) {
+            const int item = sh.tg.order[j * NT + tid] & 0xfffu;
+            if (!sh.run[item]) continue;
+            pvv::IvState o;
+            o.s = s[item];
+            o.s_left = s_left[item];
+            o.s_right = s_right[item];
+            o.mode = sh.mode[item];
+            const double ds = pvv::iv_iteration_tail(sh.x[item], sh.beta[item], sh.b_max[item], b[item], o);
+            bool running = false;
+            if (it == 0) running = pvv::iv_iteration_head(1, ds, o);
+            s[item] = o.s;
+            s_left[item] = o.s_left;
+            s_right[item] = o.s_right;
+            sh.run[item] = running;
+        }
+        __syncthreads();
     }
-    // hand the result back: a[2] / mode[] are not used by the batches
-    sh.a[2][item] = active2 ? o.s : 0.0;
-    sh.mode[item] = (unsigned char)(st2 & pvv::ST_ZERO_DIVISION);
-    __syncthreads();
-    if (sh.mode[tid]) st |= pvv::ST_ZERO_DIVISION;
-    return sh.a[2][tid];
 }
 
-template <int MODEL>
-__global__ void __launch_bounds__(kIvThreads, 2) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
+// Front of the tile in natural order (contract c = j * NT + tid, coalesced loads): implied_volatility.py:48-86
+// and the first lines of the numba loop -> x, beta, the run flag and the status bits of every contract.
+template <int MODEL, int NT, int IPT>
+__device__ __forceinline__ void iv_tile_front(IvTile<NT, IPT> &sh, long long tile0, long long n, const int8_t *__restrict__ flag,
+                                              const double *__restrict__ price, const double *__restrict__ S, const double *__restrict__ K,
+                                              const double *__restrict__ t, const double *__restrict__ r, const double *__restrict__ q,
+                                              const Strides &st) {
+    const int tid = threadIdx.x;
+    if (tid < pvv::kSortKeys) {
+        sh.ts.cnt[tid] = 0;
+        sh.tg.cnt[tid] = 0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < IPT; ++j) {
+        const int c = j * NT + tid;
+        const long long i = tile0 + c;
+        unsigned status = 0;
+        pvv::IvFront fr;
+        fr.beta = 0.0;
+        fr.x = 0.0;
+        if (i < n) {
+            const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
+            fr = pvv::iv_front<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
+                                      r[i * st.s[5]], qq, status);
+        }
+        sh.x[c] = fr.x;
+        sh.beta[c] = fr.beta;
+        sh.run[c] = (i < n) && !(fr.beta <= 0);  // beta <= 0: the reference returns 0 without solving
+        sh.zde[c] = 0;
+        sh.stat[c] = (unsigned char)status;
+    }
+}
+
+// sigma = s / sqrt(t) with the on_error mask, and the final status byte of contract c
+template <int NT, int IPT>
+__device__ __forceinline__ double iv_tile_vol(const IvTile<NT, IPT> &sh, int c, double ti, int mask_errors, unsigned &status) {
+    status = sh.stat[c];
+    if (sh.zde[c]) status |= pvv::ST_ZERO_DIVISION;
+    const double vol = sh.q[0][c] / sqrt(ti);
+    return (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) ? pvv::u2d(0x7ff8000000000000ull) : vol;
+}
+
+// K3 comes in two shapes with 3 contracts per thread: 1024 threads (one CTA per SM, 3072 contracts, 216 KB of
+// shared memory) for long columns, 512 threads (two CTAs per SM, 1536 contracts each) for short ones, where the
+// last wave of big tiles would leave most SMs idle (the host pipeline's 512 Ki-contract chunks are 171 big tiles).
+constexpr int kIvIpt = 3;
+constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * kIvIpt;  // at least four full waves of big tiles
+
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
                                                            const double *__restrict__ S, const double *__restrict__ K,
                                                            const double *__restrict__ t, const double *__restrict__ r,
                                                            const double *__restrict__ q, Strides st, int mask_errors,
                                                            double *__restrict__ iv, uint8_t *__restrict__ status_out, long long *first_zde,
                                                            long long base) {
-    __shared__ IvShared sh;
-    pvv::tile_sort_init(sh.ts);
-    const long long i = (long long)blockIdx.x * kIvThreads + threadIdx.x;
-    const bool valid = i < n;
-    unsigned status = 0;
-    pvv::IvFront fr;
-    fr.beta = 0.0;
-    fr.x = 0.0;
-    fr.sqrt_t = 1.0;
-    if (valid) {
-        const double qq = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
-        fr = pvv::iv_front<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
-                                  r[i * st.s[5]], qq, status);
+    using Tile = IvTile<NT, kIvIpt>;
+    Tile &sh = *reinterpret_cast<Tile *>(dyn_smem);
+    const long long tile0 = (long long)blockIdx.x * Tile::C;
+    iv_tile_front<MODEL>(sh, tile0, n, flag, price, S, K, t, r, q, st);
+    iv_tile_solve2(sh);
+#pragma unroll 1
+    for (int j = 0; j < kIvIpt; ++j) {
+        const int c = j * NT + threadIdx.x;
+        const long long i = tile0 + c;
+        if (i >= n) continue;
+        unsigned status;
+        iv[i] = iv_tile_vol(sh, c, t[i * st.s[4]], mask_errors, status);
+        if (status_out) status_out[i] = (uint8_t)status;
+        if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     }
-    const double s = iv_tile_solve(sh, fr.beta, fr.x, valid, status);
-    if (!valid) return;
-    double vol = s / fr.sqrt_t;
-    if (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) vol = pvv::u2d(0x7ff8000000000000ull);
-    iv[i] = vol;
-    if (status_out) status_out[i] = (uint8_t)status;
-    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
 }
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
-// One CTA = 512 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2 runs the K2
-// tile machinery twice, 256 contracts (2048 stencil items, 84 KB of dynamic shared memory) at a time, over
-// the same shared memory: all 512 threads stage (two per contract) and each evaluates 4 sorted items.
-// (1024-item sub-tiles, where half the threads idle during staging: 1.87 -> 2.14 G contracts/s.)
+// One CTA = 512 threads, 1536 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2
+// runs the K2 tile machinery six times, 256 contracts (2048 stencil items) at a time, over the same
+// shared memory: all 512 threads stage (two per contract) and each evaluates 4 sorted items.
 // The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
-constexpr int kIvgItems = 2048;                 // stencil items per sub-tile of K4 (4 per thread)
-constexpr int kIvgContracts = kIvgItems / 8;    // 256 contracts per sub-tile: every thread stages one half of a contract
+constexpr int kIvgThreads = 512, kIvgIpt = 3;
+constexpr int kIvgTile = kIvgThreads * kIvgIpt;  // contracts per CTA
+constexpr int kIvgItems = 2048;                  // stencil items per sub-tile (4 per thread)
+constexpr int kIvgContracts = kIvgItems / 8;     // 256 contracts per sub-tile: every thread stages one half of a contract
+static_assert(kIvgTile % kIvgContracts == 0, "sub-tiles must cover the tile");
+using IvTile4 = IvTile<kIvgThreads, kIvgIpt>;
 struct IvGreeksShared {
     pvv::PriceItems<kIvgItems> items;
-    pvv::TileSort<kIvThreads, kIvgItems / kIvThreads> ts;
-    double vol[kIvThreads];
+    pvv::TileSort<kIvgThreads, kIvgItems / kIvgThreads> ts;
     unsigned char zf[3][kIvgContracts];  // zero-division flags of a sub-tile: staging half 0 / half 1 / evaluation
+    double vol[kIvgTile];                // phase 1 -> phase 2
+    unsigned char stat[kIvgTile];
 };
 union IvGreeksUnion {
-    IvShared iv;
+    IvTile4 iv;
     IvGreeksShared g;
 };
 
 template <int MODEL>
-__global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag,
-                                                                  const double *__restrict__ price, const double *__restrict__ S,
-                                                                  const double *__restrict__ K, const double *__restrict__ t,
-                                                                  const double *__restrict__ r, const double *__restrict__ q, Strides st,
-                                                                  int mask_errors, double *__restrict__ iv, uint8_t *__restrict__ status_out,
-                                                                  double *__restrict__ delta, double *__restrict__ gamma,
-                                                                  double *__restrict__ theta, double *__restrict__ rho,
-                                                                  double *__restrict__ vega, long long *first_zde, long long base) {
+__global__ void __launch_bounds__(kIvgThreads, 2) iv_greeks_kernel(long long n, const int8_t *__restrict__ flag,
+                                                                   const double *__restrict__ price, const double *__restrict__ S,
+                                                                   const double *__restrict__ K, const double *__restrict__ t,
+                                                                   const double *__restrict__ r, const double *__restrict__ q, Strides st,
+                                                                   int mask_errors, double *__restrict__ iv, uint8_t *__restrict__ status_out,
+                                                                   double *__restrict__ delta, double *__restrict__ gamma,
+                                                                   double *__restrict__ theta, double *__restrict__ rho,
+                                                                   double *__restrict__ vega, long long *first_zde, long long base) {
     constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
-    IvShared &sh = reinterpret_cast<IvGreeksUnion *>(dyn_smem)->iv;
+    IvTile4 &sh = reinterpret_cast<IvGreeksUnion *>(dyn_smem)->iv;
     IvGreeksShared &gs = reinterpret_cast<IvGreeksUnion *>(dyn_smem)->g;
-    pvv::tile_sort_init(sh.ts);
     const int tid = threadIdx.x;
-    const long long tile0 = (long long)blockIdx.x * kIvThreads;
-    const long long i = tile0 + tid;
-    const bool valid = i < n;
-    unsigned status = 0;
-    pvv::IvFront fr;
-    fr.beta = 0.0;
-    fr.x = 0.0;
-    fr.sqrt_t = 1.0;
-    if (valid) {
-        const double qq = BSM ? q[i * st.s[6]] : 0.0;
-        fr = pvv::iv_front<MODEL>((double)flag[i * st.s[0]], price[i * st.s[1]], S[i * st.s[2]], K[i * st.s[3]], t[i * st.s[4]],
-                                  r[i * st.s[5]], qq, status);
+    const long long tile0 = (long long)blockIdx.x * kIvgTile;
+    iv_tile_front<MODEL>(sh, tile0, n, flag, price, S, K, t, r, q, st);
+    iv_tile_solve2(sh);
+    // sigma leaves the solver's arrays through registers: phase 2's arrays overlay them
+    double vol[kIvgIpt];
+    unsigned status[kIvgIpt];
+#pragma unroll
+    for (int j = 0; j < kIvgIpt; ++j) {
+        const int c = j * kIvgThreads + tid;
+        const long long i = tile0 + c;
+        vol[j] = iv_tile_vol(sh, c, i < n ? t[i * st.s[4]] : 1.0, mask_errors, status[j]);
+        if (i < n) iv[i] = vol[j];
     }
-    const double s = iv_tile_solve(sh, fr.beta, fr.x, valid, status);
-    double vol = s / fr.sqrt_t;
-    if (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) vol = pvv::u2d(0x7ff8000000000000ull);
-    if (valid) iv[i] = vol;
-    __syncthreads();  // the solver's shared arrays are dead from here on
-    gs.vol[tid] = vol;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kIvgIpt; ++j) {
+        gs.vol[j * kIvgThreads + tid] = vol[j];
+        gs.stat[j * kIvgThreads + tid] = (unsigned char)status[j];
+    }
     pvv::tile_sort_init(gs.ts);
     const unsigned want = (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) | (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
     const unsigned need = stencil_need(want);
+    const int c = tid % kIvgContracts, half = tid / kIvgContracts;
 #pragma unroll 1
-    for (int sub = 0; sub < kIvThreads / kIvgContracts; ++sub) {
+    for (int sub = 0; sub < kIvgTile / kIvgContracts; ++sub) {
         __syncthreads();
-        const int c = tid % kIvgContracts, half = tid / kIvgContracts;
         const long long gi = tile0 + sub * kIvgContracts + c;
         const bool gvalid = gi < n;
         double Si = 0, Ki = 0, ti = 0, f = 1, ri = 0, qi = 0, sg = 0;
@@ -449,21 +525,26 @@ __global__ void __launch_bounds__(kIvThreads, 2) iv_greeks_kernel(long long n, c
             if (BSM) qi = q[gi * st.s[6]];
             sg = gs.vol[sub * kIvgContracts + c];
         }
-        {
-            unsigned sst = 0;
-            stage_greeks<BSM, kIvgItems>(gs.items, c, half, gvalid, f, Si, Ki, ti, ri, sg, qi, need, sst);
-            gs.zf[half][c] = (sst & pvv::ST_ZERO_DIVISION) ? 1 : 0;
-            if (half == 0) gs.zf[2][c] = 0;
-        }
+        unsigned sst = 0;
+        stage_greeks<BSM, kIvgItems>(gs.items, c, half, gvalid, f, Si, Ki, ti, ri, sg, qi, need, sst);
+        gs.zf[half][c] = (sst & pvv::ST_ZERO_DIVISION) ? 1 : 0;
+        if (half == 0) gs.zf[2][c] = 0;
         __syncthreads();  // the sort classifies items staged by other threads
-        pvv::eval_price_items<kIvThreads, kIvgItems / kIvThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kIvgContracts] = 1; });
+        pvv::eval_price_items<kIvgThreads, kIvgItems / kIvgThreads, true>(gs.items, gs.ts, [&](int item) { gs.zf[2][item % kIvgContracts] = 1; });
         if (gvalid && half == 0) finish_greeks(gs.items, c, gi, f, Si, Ki, ti, nullptr, delta, gamma, theta, rho, vega);
         __syncthreads();  // zf[2] written during the evaluation
-        if (tid / kIvgContracts == sub && (gs.zf[0][c] | gs.zf[1][c] | gs.zf[2][c])) status |= pvv::ST_ZERO_DIVISION;  // owner thread
+        if (half == 0 && (gs.zf[0][c] | gs.zf[1][c] | gs.zf[2][c])) gs.stat[sub * kIvgContracts + c] |= (unsigned char)pvv::ST_ZERO_DIVISION;
     }
-    if (!valid) return;
-    if (status_out) status_out[i] = (uint8_t)status;
-    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kIvgIpt; ++j) {
+        const int cc = j * kIvgThreads + tid;
+        const long long i = tile0 + cc;
+        if (i >= n) continue;
+        const unsigned stt = gs.stat[cc];
+        if (status_out) status_out[i] = (uint8_t)stt;
+        if (stt & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    }
 }
 
 // ---- diagnostics ---------------------------------------------------------------------------------
@@ -517,6 +598,21 @@ inline int grid_tiles(long long n, int per_cta) { return (int)((n + per_cta - 1)
 template <class Kern>
 inline void allow_smem(Kern k, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int MODEL>
+inline void launch_iv_shape(long long n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
+                            const double *r, const double *q, const Strides &st, int mask_errors, double *iv, uint8_t *status, long long *fz,
+                            long long base, cudaStream_t s) {
+    if (n >= kIvBigTileMin) {
+        using Tile = IvTile<1024, kIvIpt>;
+        allow_smem(iv_kernel<MODEL, 1024>, sizeof(Tile));
+        iv_kernel<MODEL, 1024><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    } else {
+        using Tile = IvTile<512, kIvIpt>;
+        allow_smem(iv_kernel<MODEL, 512>, sizeof(Tile));
+        iv_kernel<MODEL, 512><<<grid_tiles(n, Tile::C), 512, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    }
 }
 
 inline bool fill_strides(const int64_t *stride, Strides &out) {
@@ -593,9 +689,9 @@ static int launch_iv(int model, int64_t n, const int8_t *flag, const double *pri
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 0) iv_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
-    else if (model == 1) iv_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
-    else iv_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, 0, s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+    if (model == 0) launch_iv_shape<0>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
+    else if (model == 1) launch_iv_shape<1>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
+    else launch_iv_shape<2>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
     g_launches++;
     return launch_status();
 }
@@ -611,11 +707,11 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
-        { allow_smem(iv_greeks_kernel<0>, sizeof(IvGreeksUnion)); iv_greeks_kernel<0><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
+        { allow_smem(iv_greeks_kernel<0>, sizeof(IvGreeksUnion)); iv_greeks_kernel<0><<<grid_tiles(n, kIvgTile), kIvgThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     else if (model == 1)
-        { allow_smem(iv_greeks_kernel<1>, sizeof(IvGreeksUnion)); iv_greeks_kernel<1><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
+        { allow_smem(iv_greeks_kernel<1>, sizeof(IvGreeksUnion)); iv_greeks_kernel<1><<<grid_tiles(n, kIvgTile), kIvgThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     else
-        { allow_smem(iv_greeks_kernel<2>, sizeof(IvGreeksUnion)); iv_greeks_kernel<2><<<grid_tiles(n, kIvThreads), kIvThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
+        { allow_smem(iv_greeks_kernel<2>, sizeof(IvGreeksUnion)); iv_greeks_kernel<2><<<grid_tiles(n, kIvgTile), kIvgThreads, sizeof(IvGreeksUnion), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, delta, gamma, theta, rho, vega, fz, base); }
     g_launches++;
     return launch_status();
 }
