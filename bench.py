@@ -77,15 +77,17 @@ def make_chain(workload, n, seed, pricer=None):
     return chain_cfg2(n, seed=seed)
 
 
-# DP instructions (DFMA+DMUL+DADD+DSETP, thread level, divergence included) per contract, from the ncu
-# captures under profiles/ (smsp__inst_executed by opcode x 32 / contracts); used for the fp64 fraction
-DP_INST_PER_CONTRACT = {"greeks": 2620.0, "price": 364.0, "iv": 1789.0, "iv_greeks": 4308.0, "surface": 2620.0 + 364.0, "analytic": 267.0}
+# DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01g_ncu_full_summary.txt:
+#   algorithmic = executed on ACTIVE lanes (the work the reference's formulas need; invariant under regrouping),
+#   slots       = warp-level issues x 32 / contracts (what occupies the FP64 pipe, inactive lanes included).
+DP_INST_PER_CONTRACT = {"greeks": 1848.0, "price": 255.0, "iv": 1319.0, "iv_greeks": 3145.0, "surface": 1848.0 + 255.0, "analytic": 267.0}
+DP_SLOTS_PER_CONTRACT = {"greeks": 2132.0, "price": 301.0, "iv": 1473.0, "iv_greeks": 3541.0, "surface": 2132.0 + 301.0, "analytic": 267.0}
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the ncu --set full
-# captures under profiles/r01_final_ncu_full_summary.txt; below the algorithmic bytes because the outputs of
-# a launch are still resident in the 126 MB L2 when the kernel ends
-TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 47.2, "price": 41.1, "iv": 54.4, "iv_greeks": 72.7, "analytic": 76.8, "surface": 47.2 + 41.1}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the same ncu --set full
+# captures.  K1/K2 stay below the algorithmic bytes (the outputs of a launch are still in the 126 MB L2 when the
+# kernel ends); K3/K4 exceed them by their register-spill traffic and the second read of t (HBM is 5 % busy).
+TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 46.0, "price": 41.1, "iv": 68.9, "iv_greeks": 134.1, "analytic": 76.8, "surface": 46.0 + 41.1}
 
 
 class ClockSampler:
@@ -415,9 +417,11 @@ def main():
                          "note": ("closed-form kernel: HBM is the binding roofline" if wl == "analytic" else "kernel is FP64-pipe bound, not HBM bound (SURVEY.md 8(d)); see fp64")},
             "fp64": {"achieved_dp_inst_per_s": value / world * DP_INST_PER_CONTRACT[wl], "peak_dp_inst_per_s_nofma": fp64_peak,
                      "peak_dp_inst_per_s_fma": fp64_peak_fma, "frac": value / world * DP_INST_PER_CONTRACT[wl] / fp64_peak,
-                     "dp_inst_per_contract": DP_INST_PER_CONTRACT[wl],
-                     "how": "peak: dependent DMUL+DADD (and DFMA) chains, 8 per thread, measured in this run; "
-                            "achieved: contracts/s x DP instructions per contract counted by ncu (profiles/)"},
+                     "pipe_frac": value / world * DP_SLOTS_PER_CONTRACT[wl] / fp64_peak,
+                     "dp_inst_per_contract": DP_INST_PER_CONTRACT[wl], "dp_slots_per_contract": DP_SLOTS_PER_CONTRACT[wl],
+                     "how": "peak: dependent DMUL+DADD (and DFMA) chains, 8 per thread, measured in this run; frac: contracts/s x DP "
+                            "instructions per contract executed on active lanes (ncu, profiles/) / peak; pipe_frac: the same with "
+                            "warp-level issues x 32 (inactive lanes occupy the pipe too; compare sm__pipe_fp64_cycles_active)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, model)

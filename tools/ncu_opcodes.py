@@ -32,6 +32,8 @@ tot, ts = sum(ops.values()), sum(samples.values())
 dp = sum(ops[k] for k in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"))
 print(f"{rep}: warp instructions {tot}, DP {dp} ({dp / tot * 100:.1f}%), active threads/instr {sum(thr.values()) / tot:.2f}")
 if contracts:
-    print(f"per contract: {tot * 32 / contracts:.0f} thread-instruction slots, {dp * 32 / contracts:.0f} DP slots")
+    dpt = sum(thr[k] for k in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"))
+    print(f"per contract: {tot * 32 / contracts:.0f} thread-instruction slots, {dp * 32 / contracts:.0f} DP slots (warp-level x 32: what occupies the pipe), "
+          f"{dpt / contracts:.0f} DP instructions on active lanes (the algorithmic work)")
 for k, v in ops.most_common(24):
     print(f"  {k:14s} {v:12d} {v / tot * 100:5.1f}%   stall samples {samples[k] / max(ts, 1) * 100:5.1f}%")
