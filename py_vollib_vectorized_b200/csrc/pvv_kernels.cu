@@ -276,7 +276,7 @@ template <int NT, int IPT>
 struct IvTile {
     static constexpr int C = NT * IPT;
     double x[C], beta[C], b_max[C];
-    double q[5][C];             // until the guess: s_c, b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, ds, b
+    double q[5][C];             // until the guess: s_c, b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, -, b
     unsigned char run[C];       // the contract takes part in the current batch
     unsigned char mode[C];      // iteration objective (MODE_*)
     unsigned char zde[C];       // a batch evaluation divided by zero
@@ -331,7 +331,7 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     // initial guess, contracts regrouped by branch.  From here on thread (j, tid) works on contract
     // tg.order[j * NT + tid]: the tile stays grouped by solver branch through the Householder passes.
     pvv::tile_sort(sh.tg, [&](int c) { return sh.run[c] ? pvv::iv_branch(sh.beta[c], b_c[c], b_2[c]) : (int)pvv::IV_DONE; });
-    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *dsa = sh.q[3], *b = sh.q[4];
+    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *b = sh.q[4];
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.tg.order[j * NT + tid];
@@ -349,7 +349,6 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
         s[item] = o.s;  // the item's inputs are consumed: its slots become the iteration state
         s_left[item] = o.s_left;
         s_right[item] = o.s_right;
-        dsa[item] = -DBL_MAX;
         sh.mode[item] = (unsigned char)o.mode;
         sh.run[item] = running;
     }
