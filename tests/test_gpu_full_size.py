@@ -84,6 +84,33 @@ def test_cfg3_ten_million_iv_with_strata(eng, oracle):
     assert (stt.cpu().numpy() == status).all()
 
 
+def test_iv_big_and_small_tile_shapes_agree_on_ragged_sizes(eng, oracle):
+    """K3 has two launch shapes (3072-contract tiles from 1 818 624 contracts on, 1536-contract tiles below):
+    a ragged column just above the switch through the device path (big tiles, partial last tile) must equal the
+    host pipeline (chunks -> small tiles) and the oracle bit for bit, for all three models."""
+    import torch
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    n = 4 * 148 * 3072 + 1234
+    c = chain_cfg2(n, seed=5)
+    th = oracle.max_threads
+    for model in ("black", "black_scholes", "black_scholes_merton"):
+        bsm = model == "black_scholes_merton"
+        q = col(c["q"]) if bsm else None
+        r = None if model == "black" else col(c["r"])
+        price = eng.price(model, n, col(c["flag"]), col(c["S"]), col(c["K"]), col(c["t"]), r, q, col(c["sigma"]))
+        price[::97] *= 0.5  # some rows below intrinsic / far from the clean price
+        iv_h, st_h, _ = eng.iv(model, n, col(c["flag"]), col(price), col(c["S"]), col(c["K"]), col(c["t"]), col(c["r"]), q)
+        d = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in ("flag", "S", "K", "t", "r", "q")}
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        stt = torch.empty(n, dtype=torch.uint8, device="cuda")
+        eng.iv_dev(model, n, d["flag"], torch.from_numpy(price).cuda(), d["S"], d["K"], d["t"], d["r"], d["q"] if bsm else None, out, stt)
+        assert_bit_equal(iv_h, out.cpu().numpy(), f"{model}: big tiles vs small tiles")
+        assert (stt.cpu().numpy() == st_h).all()
+        ref, st_ref, _ = oracle.iv(model, price, c["S"], c["K"], c["t"], c["r"], c["flag"], c["q"] if bsm else None, threads=th)
+        assert_bit_equal(ref, iv_h, f"{model}: vs oracle")
+        assert (st_ref == st_h).all()
+
+
 def test_cfg4_fused_iv_greeks_two_million(eng, oracle):
     from py_vollib_vectorized_b200.util.chains import chain_cfg2
     n = 2_000_000
