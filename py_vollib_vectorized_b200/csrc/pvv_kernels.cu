@@ -295,9 +295,9 @@ __device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, const double 
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.ts.order[j * NT + tid];
         const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
-        unsigned st2 = 0;
-        out[item] = pvv::nbc_eval(region, sh.x[item], sarr[item], st2);
-        if (st2) sh.zde[item] = 1;
+        const double xi = sh.x[item], si = sarr[item];
+        if (pvv::nbc_zde(region, xi, si)) sh.zde[item] = 1;
+        out[item] = pvv::nbc_eval(region, xi, si);
     }
     __syncthreads();
 }

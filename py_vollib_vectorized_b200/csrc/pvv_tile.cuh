@@ -117,14 +117,15 @@ __device__ __forceinline__ void eval_price_items(PriceItems<NT * IPT> &it, TileS
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = ts.order[j * NT + tid];
         const int item = e & 0xfffu, region = key_region(e >> 12);
-        unsigned st = 0;
-        const double nb = nbc_eval(region, it.x[item], it.s[item], st);
+        const double xi = it.x[item], si = it.s[item];
+        const bool zde = nbc_zde(region, xi, si);  // before the call: one predicate, not two doubles, lives across it
+        const double nb = nbc_eval(region, xi, si);
         const double tv = it.scale[item] * nb;
         const double is = it.intr[item];
         double v = (is < 0) ? (-is) + np_maximum(0.0, tv) : np_maximum(is, tv);
         if (DEFLATE) v = v * it.defl[item];
         it.x[item] = v;
-        if (st & ST_ZERO_DIVISION) on_zde(item);
+        if (zde) on_zde(item);
     }
     __syncthreads();
 }
