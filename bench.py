@@ -80,8 +80,8 @@ def make_chain(workload, n, seed, pricer=None):
 # DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01h_ncu_full_summary.txt:
 #   algorithmic = executed on ACTIVE lanes (the work the reference's formulas need; invariant under regrouping),
 #   slots       = warp-level issues x 32 / contracts (what occupies the FP64 pipe, inactive lanes included).
-DP_INST_PER_CONTRACT = {"greeks": 1839.0, "price": 254.0, "iv": 1324.0, "iv_greeks": 3142.0, "surface": 1839.0 + 254.0, "analytic": 267.0}
-DP_SLOTS_PER_CONTRACT = {"greeks": 2123.0, "price": 300.0, "iv": 1465.0, "iv_greeks": 3527.0, "surface": 2123.0 + 300.0, "analytic": 267.0}
+DP_INST_PER_CONTRACT = {"greeks": 1839.0, "price": 254.0, "iv": 1324.0, "iv_greeks": 3142.0, "surface": 1839.0 + 254.0, "analytic": 181.0}
+DP_SLOTS_PER_CONTRACT = {"greeks": 2123.0, "price": 300.0, "iv": 1465.0, "iv_greeks": 3527.0, "surface": 2123.0 + 300.0, "analytic": 230.0}
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the same ncu --set full

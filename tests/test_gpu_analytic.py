@@ -70,3 +70,34 @@ def test_analytic_greeks_regression_table(golden):
         pvv.get_all_greeks(['c'], 100, 100, .5, .01, .2, model="black", method="analytical")
     with pytest.raises(ValueError):
         pvv.get_all_greeks(['c'], 100, 100, .5, .01, .2, method="exact")
+
+
+@pytest.mark.parametrize("model", ["black_scholes", "black_scholes_merton"])
+def test_analytic_streaming_and_general_forms_agree(eng, model):
+    """The dense, 16-byte-aligned, all-outputs call runs the two-contracts-per-thread streaming kernel (128-bit
+    accesses); an odd length leaves one contract to the general kernel, and misaligned or broadcast columns or a
+    missing output take the general kernel for the whole call.  Same arithmetic: identical bits."""
+    import torch
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    n = 200_001  # odd: streaming form + one-contract tail
+    c = chain_cfg2(n + 1, seed=9)
+    d = {k: torch.from_numpy(np.ascontiguousarray(c[k])).cuda() for k in ("flag", "S", "K", "t", "r", "q", "sigma")}
+    bsm = model == "black_scholes_merton"
+
+    def run(sl, names=NAMES, align_out=True):
+        m = sl.stop - sl.start
+        outs = {k: torch.empty(m + 1, dtype=torch.float64, device="cuda")[(0 if align_out else 1):][:m] for k in names}
+        eng.analytic_greeks_dev(model, m, d["flag"][sl], d["S"][sl], d["K"][sl], d["t"][sl], d["r"][sl], d["q"][sl] if bsm else None,
+                                d["sigma"][sl], outs)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in outs.items()}
+
+    fast = run(slice(0, n))                        # aligned inputs and outputs: streaming + tail
+    shifted = run(slice(1, n))                     # inputs start 8 bytes (flag: 1 byte) off alignment: general form
+    no_price = run(slice(0, n), names=NAMES[1:])   # one output not wanted: general form
+    odd_out = run(slice(0, n), align_out=False)    # outputs off alignment: general form
+    for k in NAMES:
+        assert np.array_equal(fast[k][1:], shifted[k], equal_nan=True), k
+        assert np.array_equal(fast[k], odd_out[k], equal_nan=True), k
+        if k != "price":
+            assert np.array_equal(fast[k], no_price[k], equal_nan=True), k
