@@ -77,17 +77,17 @@ def make_chain(workload, n, seed, pricer=None):
     return chain_cfg2(n, seed=seed)
 
 
-# DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01h_ncu_full_summary.txt:
+# DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01i_ncu_full_summary.txt:
 #   algorithmic = executed on ACTIVE lanes (the work the reference's formulas need; invariant under regrouping),
 #   slots       = warp-level issues x 32 / contracts (what occupies the FP64 pipe, inactive lanes included).
-DP_INST_PER_CONTRACT = {"greeks": 1839.0, "price": 254.0, "iv": 1324.0, "iv_greeks": 3142.0, "surface": 1839.0 + 254.0, "analytic": 181.0}
-DP_SLOTS_PER_CONTRACT = {"greeks": 2123.0, "price": 300.0, "iv": 1465.0, "iv_greeks": 3527.0, "surface": 2123.0 + 300.0, "analytic": 230.0}
+DP_INST_PER_CONTRACT = {"greeks": 1839.0, "price": 254.0, "iv": 1314.0, "iv_greeks": 3131.0, "surface": 1839.0 + 254.0, "analytic": 174.0}
+DP_SLOTS_PER_CONTRACT = {"greeks": 2123.0, "price": 300.0, "iv": 1459.0, "iv_greeks": 3516.0, "surface": 2123.0 + 300.0, "analytic": 223.0}
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the same ncu --set full
 # captures.  K1/K2 stay below the algorithmic bytes (the outputs of a launch are still in the 126 MB L2 when the
 # kernel ends); K3/K4 exceed them by their register-spill traffic and the second read of t (HBM is 5 % busy).
-TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 48.5, "price": 41.1, "iv": 70.9, "iv_greeks": 143.3, "analytic": 76.8, "surface": 48.5 + 41.1}
+TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 45.7, "price": 41.1, "iv": 69.7, "iv_greeks": 139.6, "analytic": 76.6, "surface": 45.7 + 41.1}
 
 
 class ClockSampler:
