@@ -130,10 +130,16 @@ PVV_API int64_t pvv_launch_count(void);
  * the Python host to encode an object-dtype flag column ('c'/'p' singletons) in one threaded pass;
  * replaces the per-element dict lookup of util/data_format.py:10-11. */
 PVV_API int64_t pvv_match_u64(int64_t n, const uint64_t *in, int nkeys, const uint64_t *keys, const int8_t *vals, int8_t *out, int threads);
+/* the same over 4-byte cells: numpy '<U1' flag arrays (one UCS4 code point per cell), int32 / float32 flags */
+PVV_API int64_t pvv_match_u32(int64_t n, const uint32_t *in, int nkeys, const uint32_t *keys, const int8_t *vals, int8_t *out, int threads);
 
 /* out[i] = lut[in[i]] (256-entry table) for flag columns that arrive as one byte per cell; returns the
  * number of zeros written. */
 PVV_API int64_t pvv_lut_u8(int64_t n, const uint8_t *in, const int8_t *lut, int8_t *out, int threads);
+
+/* 1 if every cell of an Arrow string column is exactly one byte long (offsets[i + 1] - offsets[i] == 1 for all
+ * i < n; width = 4 or 8 bytes per offset): its data buffer then is the flag column for pvv_lut_u8. */
+PVV_API int pvv_unit_offsets(int64_t n, const void *offsets, int width, int threads);
 
 /* ---- diagnostics used by the parity tests ----------------------------------------------------- */
 /* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf,

@@ -61,6 +61,10 @@ def _load():
     lib.pvv_lut_u8.argtypes = [i64, vp, vp, vp, i32]
     lib.pvv_match_u64.restype = i64
     lib.pvv_match_u64.argtypes = [i64, vp, i32, vp, vp, vp, i32]
+    lib.pvv_unit_offsets.restype = i32
+    lib.pvv_unit_offsets.argtypes = [i64, vp, i32, i32]
+    lib.pvv_match_u32.restype = i64
+    lib.pvv_match_u32.argtypes = [i64, vp, i32, vp, vp, vp, i32]
     lib.pvv_unary_dev.argtypes = [i32, i64, vp, vp, vp]
     lib.pvv_fp64_probe.argtypes = [i64, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     return lib
@@ -82,6 +86,23 @@ def match_u64(addr, n, keys, vals, out):
     k = np.ascontiguousarray(keys, dtype=np.uint64)
     v = np.ascontiguousarray(vals, dtype=np.int8)
     return int(_lib.pvv_match_u64(n, ctypes.c_void_p(addr), k.size, _hp(k), _hp(v), _hp(out), 0))
+
+
+def match_cells(arr, keys, vals, out):
+    """out[i] = vals[j] where the 4- or 8-byte cell arr[i] has the bit pattern keys[j]; returns the number of misses."""
+    if arr.dtype.itemsize == 8:
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        fn = _lib.pvv_match_u64
+    else:
+        k = np.ascontiguousarray(keys, dtype=np.uint32)
+        fn = _lib.pvv_match_u32
+    v = np.ascontiguousarray(vals, dtype=np.int8)
+    return int(fn(arr.size, ctypes.c_void_p(arr.ctypes.data), k.size, _hp(k), _hp(v), _hp(out), 0))
+
+
+def unit_offsets(offsets):
+    """True if every cell delimited by the (int32 / int64) Arrow offsets array is exactly one byte long."""
+    return bool(_lib.pvv_unit_offsets(offsets.size - 1, ctypes.c_void_p(offsets.ctypes.data), offsets.dtype.itemsize, 0))
 
 
 def lut_u8(data, lut, out):
