@@ -5,10 +5,12 @@
 //
 // Data layout in HBM: structure of arrays — one int8 flag column and one float64 column per input,
 // each either dense (stride 1) or a single broadcast scalar (stride 0); one float64 column per
-// output (+ one uint8 status column for the IV kernels).  One thread per contract, consecutive
-// threads read consecutive elements: every warp-level access is a fully coalesced 256-byte line
-// pair.  The kernels are FP64-pipe bound (hundreds to thousands of DP instructions per 50-100 bytes
-// of traffic), so the launch shape is chosen for occupancy of the FP64 pipe, not for bandwidth.
+// output (+ one uint8 status column for the IV kernels).  Consecutive threads read consecutive
+// elements: every warp-level access is a fully coalesced 256-byte line pair.  The kernels are
+// FP64-pipe bound (hundreds to thousands of DP instructions per 50-100 bytes of traffic), so the
+// launch shapes are chosen for uniform, balanced warps on the FP64 pipe, not for bandwidth: a CTA
+// stages a tile of work in shared memory, counting-sorts it by code path (pvv_tile.cuh) and
+// evaluates it in sorted order, several items per thread.  DESIGN.md section 5 has the measurements.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -47,7 +49,7 @@ constexpr int kItemsPerThread = 4;
 constexpr int kTileItems = kTileThreads * kItemsPerThread;
 constexpr int kGreekContracts = kTileItems / 8;  // contracts per CTA of the greeks kernel: 8 stencil points each
 
-// shared memory of K1 / K2 (dynamic: above 48 KB for 512-thread tiles)
+// shared memory of K1 / K2 (43 KB; dynamic like the larger tiles of K3 / K4)
 struct PriceTileShared {
     pvv::PriceItems<kTileItems> items;
     pvv::TileSort<kTileThreads, kItemsPerThread> ts;
