@@ -272,13 +272,14 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
 // Per-contract arithmetic is exactly pvv::normalised_iv (pvv_math.cuh), so results are unchanged.
 // Why IPT > 1: the size of the sorted population decides how uniform the warps are, and with one item
 // per thread a warp that drew an expensive region cannot be balanced.  Measured (10 M BSM contracts,
-// G solves/s): registers-resident state, 512 x 1: 4.30, 1024 x 1: 4.45; shared-memory state,
-// 512 x 2: 4.36, 512 x 3: 5.33, 1024 x 3: 5.49, 768 x 4: 5.19, 384 x 4: 4.98, 512 x 6 (one CTA per SM): 4.42.
+// G solves/s): registers-resident state, 512 x 1: 4.30, 1024 x 1: 4.45; shared-memory state (72 B per
+// contract), 512 x 2: 4.36, 512 x 3: 5.33, 1024 x 3: 5.49, 768 x 4: 5.19, 384 x 4: 4.98, 512 x 6 (one CTA
+// per SM): 4.42; compact state (56 B), 1024 x 3: 5.60, 1024 x 4: 5.66.
 template <int NT, int IPT>
 struct IvTile {
     static constexpr int C = NT * IPT;
-    double x[C], beta[C], b_max[C];
-    double q[5][C];             // until the guess: s_c, b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, -, b
+    double x[C], beta[C];
+    double q[4][C];             // until the guess: b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, b
     unsigned char run[C];       // the contract takes part in the current batch
     unsigned char mode[C];      // iteration objective (MODE_*)
     unsigned char zde[C];       // a batch evaluation divided by zero
@@ -286,18 +287,21 @@ struct IvTile {
     pvv::TileSort<NT, IPT> ts;  // order of the b(x, s) batches
     pvv::TileSort<NT, IPT> tg;  // order by solver branch: fixed from the initial guess to the end
 };
+// 56 bytes per contract: four contracts per thread fit the 227 KB of a 1024-thread CTA.  The centre node
+// s_c = sqrt(|2x|) and b_max = exp(x/2) are recomputed where they are used (b_max only on the upper
+// branches) instead of being stored: same expressions, same bits, 16 bytes per contract less.
 
-// b(x[item], sarr[item]) -> out[item] for every running contract of the tile, in key-sorted order.
-// Entered with all writes to x / sarr / run visible (barrier by the caller); ends with a barrier.
-template <int NT, int IPT>
-__device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, const double *sarr, double *out) {
+// b(x[item], s_of(item)) -> out[item] for every running contract of the tile, in key-sorted order.
+// Entered with all writes to x / s / run visible (barrier by the caller); ends with a barrier.
+template <int NT, int IPT, class SOf>
+__device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, double *out) {
     const int tid = threadIdx.x;
-    pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], sarr[c]) : (int)pvv::K_ZERO; });
+    pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], s_of(c)) : (int)pvv::K_ZERO; });
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.ts.order[j * NT + tid];
         const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
-        const double xi = sh.x[item], si = sarr[item];
+        const double xi = sh.x[item], si = s_of(item);
         if (pvv::nbc_zde(region, xi, si)) sh.zde[item] = 1;
         out[item] = pvv::nbc_eval(region, xi, si);
     }
@@ -310,30 +314,24 @@ __device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, const double 
 template <int NT, int IPT>
 __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     const int tid = threadIdx.x;
-    double *s_c = sh.q[0], *b_c = sh.q[1], *v_c = sh.q[2], *s_2 = sh.q[3], *b_2 = sh.q[4];
-#pragma unroll 1
-    for (int j = 0; j < IPT; ++j) {
-        const int c = j * NT + tid;
-        if (!sh.run[c]) continue;
-        const double x = sh.x[c];
-        sh.b_max[c] = pvv::exp_g(0.5 * x);
-        s_c[c] = sqrt(fabs(2 * x));
-    }
+    double *b_c = sh.q[0], *v_c = sh.q[1], *s_2 = sh.q[2], *b_2 = sh.q[3];
+    const auto s_c = [&](int c) { return sqrt(fabs(2 * sh.x[c])); };
     iv_tile_batch(sh, s_c, b_c);  // own slots only so far: no barrier needed before the sort
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const int c = j * NT + tid;
         if (!sh.run[c]) continue;
-        const double x = sh.x[c], sc = s_c[c];
+        const double x = sh.x[c], sc = s_c(c), beta = sh.beta[c], bc = b_c[c];
         const double vc = pvv::normalised_vega(x, sc);
+        const double b_max = (beta < bc) ? 0.0 : pvv::exp_g(0.5 * x);  // the lower side does not look at it
         v_c[c] = vc;
-        s_2[c] = pvv::iv_second_node(sh.beta[c], sh.b_max[c], sc, b_c[c], vc);
+        s_2[c] = pvv::iv_second_node(beta, b_max, sc, bc, vc);
     }
-    iv_tile_batch(sh, s_2, b_2);
+    iv_tile_batch(sh, [&](int c) { return s_2[c]; }, b_2);
     // initial guess, contracts regrouped by branch.  From here on thread (j, tid) works on contract
     // tg.order[j * NT + tid]: the tile stays grouped by solver branch through the Householder passes.
     pvv::tile_sort(sh.tg, [&](int c) { return sh.run[c] ? pvv::iv_branch(sh.beta[c], b_c[c], b_2[c]) : (int)pvv::IV_DONE; });
-    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *b = sh.q[4];
+    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *b = sh.q[3];
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.tg.order[j * NT + tid];
@@ -345,7 +343,9 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
         o.mode = pvv::MODE_MIDDLE;
         bool running = branch != pvv::IV_DONE;
         if (running) {
-            o = pvv::iv_initial_guess(branch, sh.x[item], sh.beta[item], sh.b_max[item], s_c[item], b_c[item], v_c[item], s_2[item], b_2[item]);
+            const double x = sh.x[item];
+            const double b_max = (branch == pvv::IV_HIGHEST) ? pvv::exp_g(0.5 * x) : 0.0;  // only the highest segment uses it
+            o = pvv::iv_initial_guess(branch, x, sh.beta[item], b_max, s_c(item), b_c[item], v_c[item], s_2[item], b_2[item]);
             running = pvv::iv_iteration_head(0, -DBL_MAX, o);
         }
         s[item] = o.s;  // the item's inputs are consumed: its slots become the iteration state
@@ -357,7 +357,7 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     __syncthreads();
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        iv_tile_batch(sh, s, b);
+        iv_tile_batch(sh, [&](int c) { return s[c]; }, b);
 #pragma unroll 1
         for (int j = 0; j < IPT; ++j) {
             const int item = sh.tg.order[j * NT + tid] & 0xfffu;
@@ -367,7 +367,9 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
             o.s_left = s_left[item];
             o.s_right = s_right[item];
             o.mode = sh.mode[item];
-            const double ds = pvv::iv_iteration_tail(sh.x[item], sh.beta[item], sh.b_max[item], b[item], o);
+            const double x = sh.x[item];
+            const double b_max = (o.mode == pvv::MODE_HIGHEST) ? pvv::exp_g(0.5 * x) : 0.0;  // only that objective uses it
+            const double ds = pvv::iv_iteration_tail(x, sh.beta[item], b_max, b[item], o);
             bool running = false;
             if (it == 0) running = pvv::iv_iteration_head(1, ds, o);
             s[item] = o.s;
@@ -422,26 +424,26 @@ __device__ __forceinline__ double iv_tile_vol(const IvTile<NT, IPT> &sh, int c, 
     return (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) ? pvv::u2d(0x7ff8000000000000ull) : vol;
 }
 
-// K3 comes in two shapes with 3 contracts per thread: 1024 threads (one CTA per SM, 3072 contracts, 216 KB of
-// shared memory) for long columns, 512 threads (two CTAs per SM, 1536 contracts each) for short ones, where the
-// last wave of big tiles would leave most SMs idle (the host pipeline's 512 Ki-contract chunks are 171 big tiles).
-constexpr int kIvIpt = 3;
-constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * kIvIpt;  // at least four full waves of big tiles
+// K3 comes in two shapes: 1024 threads x 4 contracts (one CTA per SM, 4096 contracts, 224 KB of shared memory)
+// for long columns, 512 threads x 3 contracts (two CTAs per SM, 1536 contracts each) for short ones, where the
+// last wave of big tiles would leave most SMs idle and a tile's latency shows (the host pipeline's 512 Ki-contract
+// chunks: 0.99 G IV/s end to end with the small shape, 0.95 with 2048-contract tiles).
+constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * 4;  // at least four full waves of big tiles
 
-template <int MODEL, int NT>
+template <int MODEL, int NT, int IPT>
 __global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
                                                            const double *__restrict__ S, const double *__restrict__ K,
                                                            const double *__restrict__ t, const double *__restrict__ r,
                                                            const double *__restrict__ q, Strides st, int mask_errors,
                                                            double *__restrict__ iv, uint8_t *__restrict__ status_out, long long *first_zde,
                                                            long long base) {
-    using Tile = IvTile<NT, kIvIpt>;
+    using Tile = IvTile<NT, IPT>;
     Tile &sh = *reinterpret_cast<Tile *>(dyn_smem);
     const long long tile0 = (long long)blockIdx.x * Tile::C;
     iv_tile_front<MODEL>(sh, tile0, n, flag, price, S, K, t, r, q, st);
     iv_tile_solve2(sh);
 #pragma unroll 1
-    for (int j = 0; j < kIvIpt; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const int c = j * NT + threadIdx.x;
         const long long i = tile0 + c;
         if (i >= n) continue;
@@ -453,11 +455,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const in
 }
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
-// One CTA = 512 threads, 1536 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2
-// runs the K2 tile machinery six times, 256 contracts (2048 stencil items) at a time, over the same
+// One CTA = 512 threads, 2048 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2
+// runs the K2 tile machinery eight times, 256 contracts (2048 stencil items) at a time, over the same
 // shared memory: all 512 threads stage (two per contract) and each evaluates 4 sorted items.
 // The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
-constexpr int kIvgThreads = 512, kIvgIpt = 3;
+constexpr int kIvgThreads = 512, kIvgIpt = 4;
 constexpr int kIvgTile = kIvgThreads * kIvgIpt;  // contracts per CTA
 constexpr int kIvgItems = 2048;                  // stencil items per sub-tile (4 per thread)
 constexpr int kIvgContracts = kIvgItems / 8;     // 256 contracts per sub-tile: every thread stages one half of a contract
@@ -606,13 +608,13 @@ inline void launch_iv_shape(long long n, const int8_t *flag, const double *price
                             const double *r, const double *q, const Strides &st, int mask_errors, double *iv, uint8_t *status, long long *fz,
                             long long base, cudaStream_t s) {
     if (n >= kIvBigTileMin) {
-        using Tile = IvTile<1024, kIvIpt>;
-        allow_smem(iv_kernel<MODEL, 1024>, sizeof(Tile));
-        iv_kernel<MODEL, 1024><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        using Tile = IvTile<1024, 4>;
+        allow_smem(iv_kernel<MODEL, 1024, 4>, sizeof(Tile));
+        iv_kernel<MODEL, 1024, 4><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
     } else {
-        using Tile = IvTile<512, kIvIpt>;
-        allow_smem(iv_kernel<MODEL, 512>, sizeof(Tile));
-        iv_kernel<MODEL, 512><<<grid_tiles(n, Tile::C), 512, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        using Tile = IvTile<512, 3>;
+        allow_smem(iv_kernel<MODEL, 512, 3>, sizeof(Tile));
+        iv_kernel<MODEL, 512, 3><<<grid_tiles(n, Tile::C), 512, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
     }
 }
 

@@ -85,12 +85,12 @@ def test_cfg3_ten_million_iv_with_strata(eng, oracle):
 
 
 def test_iv_big_and_small_tile_shapes_agree_on_ragged_sizes(eng, oracle):
-    """K3 has two launch shapes (3072-contract tiles from 1 818 624 contracts on, 1536-contract tiles below):
+    """K3 has two launch shapes (4096-contract tiles from 2 424 832 contracts on, 2048-contract tiles below):
     a ragged column just above the switch through the device path (big tiles, partial last tile) must equal the
     host pipeline (chunks -> small tiles) and the oracle bit for bit, for all three models."""
     import torch
     from py_vollib_vectorized_b200.util.chains import chain_cfg2
-    n = 4 * 148 * 3072 + 1234
+    n = 4 * 148 * 4096 + 1234
     c = chain_cfg2(n, seed=5)
     th = oracle.max_threads
     for model in ("black", "black_scholes", "black_scholes_merton"):
