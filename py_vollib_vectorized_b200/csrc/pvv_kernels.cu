@@ -56,6 +56,23 @@ struct PriceTileShared {
 };
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
+// P1 of K1 for one contract: _model_calls.py:56-67 up to the call of the undiscounted Black price
+template <int MODEL, bool BOUNDED>
+__device__ __forceinline__ void stage_price(pvv::PriceItems<kTileItems> &items, int item, double f, double Si, double Ki, double ti,
+                                            double ri, double qi, double sg, unsigned &status) {
+    double F = Si, D = 1.0;
+    if (MODEL != pvv::MODEL_BLACK) {
+        D = pvv::exp_g(-ri * ti);
+        if (MODEL == pvv::MODEL_BLACK_SCHOLES) {
+            if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
+            F = pvv::div_sel<BOUNDED>(Si, D);
+        } else {
+            F = Si * pvv::exp_g((ri - qi) * ti);
+        }
+    }
+    pvv::stage_price_item<BOUNDED>(items, item, f, F, Ki, pvv::sqrt_sel<BOUNDED>(Ki), sg * pvv::sqrt_sel<BOUNDED>(ti), D, status);
+}
+
 template <int MODEL>
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) price_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                              const double *__restrict__ K, const double *__restrict__ t,
@@ -78,19 +95,12 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) price_kernel(lon
         }
         const double f = (double)flag[i * st.s[0]];
         const double Si = S[i * st.s[1]], Ki = K[i * st.s[2]], ti = t[i * st.s[3]], sg = sigma[i * st.s[6]];
+        const double ri = (MODEL != pvv::MODEL_BLACK) ? r[i * st.s[4]] : 0.0;
+        const double qi = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : ri;
         unsigned status = 0;
-        double F = Si, D = 1.0;
-        if (MODEL != pvv::MODEL_BLACK) {
-            const double ri = r[i * st.s[4]];
-            D = pvv::exp_g(-ri * ti);
-            if (MODEL == pvv::MODEL_BLACK_SCHOLES) {
-                if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
-                F = Si / D;
-            } else {
-                F = Si * pvv::exp_g((ri - q[i * st.s[5]]) * ti);
-            }
-        }
-        pvv::stage_price_item(items, item, f, F, Ki, sqrt(Ki), sg * sqrt(ti), D, status);
+        // ordinary magnitudes (warp-uniform in practice): the guard-free divisions and square roots
+        if (pvv::staging_is_bounded(Si, Ki, ti, ri, ri - qi)) stage_price<MODEL, true>(items, item, f, Si, Ki, ti, ri, qi, sg, status);
+        else stage_price<MODEL, false>(items, item, f, Si, Ki, ti, ri, qi, sg, status);
         if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     }
     pvv::eval_price_items<kTileThreads, kItemsPerThread, MODEL != pvv::MODEL_BLACK>(
@@ -125,11 +135,14 @@ __device__ __forceinline__ unsigned stencil_need(unsigned want) {
 }
 
 // P1 for contract slot c of the tile, done by thread `half` (0: points 0,1,2,6,7; 1: points 3,4,5).
+template <bool BSM, int T, bool BOUNDED>
+__device__ __forceinline__ void stage_greeks_body(pvv::PriceItems<T> &items, int c, int half, double f, double Si, double Ki, double ti,
+                                                  double ri, double sg, double qi, unsigned need, unsigned &status);
+
 template <bool BSM, int T>
 __device__ __forceinline__ void stage_greeks(pvv::PriceItems<T> &items, int c, int half, bool valid, double f, double Si, double Ki,
                                              double ti, double ri, double sg, double qi, unsigned need, unsigned &status) {
     constexpr int kGreekContracts = T / 8;  // contracts of this tile (shadows the K2 constant: K4 uses larger sub-tiles)
-    const double dS = .01;
     if (!valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) pvv::stage_null_item(items, (half * 3 + k) * kGreekContracts + c);
@@ -139,9 +152,20 @@ __device__ __forceinline__ void stage_greeks(pvv::PriceItems<T> &items, int c, i
         }
         return;
     }
+    // contracts of ordinary magnitude (all of them, in practice) take the copy of the staging code whose divisions
+    // and square roots are the dividers' fast paths without guards; the other copy is never fetched
+    if (pvv::staging_is_bounded(Si, Ki, ti, ri, BSM ? ri - qi : 0.0)) stage_greeks_body<BSM, T, true>(items, c, half, f, Si, Ki, ti, ri, sg, qi, need, status);
+    else stage_greeks_body<BSM, T, false>(items, c, half, f, Si, Ki, ti, ri, sg, qi, need, status);
+}
+
+template <bool BSM, int T, bool BOUNDED>
+__device__ __forceinline__ void stage_greeks_body(pvv::PriceItems<T> &items, int c, int half, double f, double Si, double Ki, double ti,
+                                                  double ri, double sg, double qi, unsigned need, unsigned &status) {
+    constexpr int kGreekContracts = T / 8;
+    const double dS = .01;
     const double b = BSM ? ri - qi : ri;   // api.py:241: b = r - q on the host side of the reference
     const double qe = BSM ? ri - b : 0.0;  // _numerical_greeks.py: black_scholes_merton(..., r - b)
-    const double sqrtK = sqrt(Ki), sqrtT = sqrt(ti);
+    const double sqrtK = pvv::sqrt_sel<BOUNDED>(Ki), sqrtT = pvv::sqrt_sel<BOUNDED>(ti);
     double D0 = 0.0, g0 = 0.0;
 #pragma unroll 1
     for (int k = 0; k < 3; ++k) {
@@ -163,7 +187,7 @@ __device__ __forceinline__ void stage_greeks(pvv::PriceItems<T> &items, int c, i
         double D, F;
         if (e == 1 || e == 2) {  // same deflater (and carry factor) as the base point
             D = D0;
-            F = BSM ? Se * g0 : Se / D0;
+            F = BSM ? Se * g0 : pvv::div_sel<BOUNDED>(Se, D0);
         } else {
             D = pvv::exp_g(-re * te);
             if (BSM) {
@@ -172,12 +196,12 @@ __device__ __forceinline__ void stage_greeks(pvv::PriceItems<T> &items, int c, i
                 if (e == 0) g0 = g;
             } else {
                 if (D == 0.0) status |= pvv::ST_ZERO_DIVISION;
-                F = Se / D;
+                F = pvv::div_sel<BOUNDED>(Se, D);
             }
             if (e == 0) D0 = D;
         }
-        const double sq = (e == 3) ? sqrt(te) : sqrtT;
-        pvv::stage_price_item(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
+        const double sq = (e == 3) ? pvv::sqrt_sel<BOUNDED>(te) : sqrtT;
+        pvv::stage_price_item<BOUNDED>(items, item, f, F, Ki, sqrtK, sg * sq, D, status);
         if (e == 0) {  // sigma +- 0.01: same forward, only s changes
 #pragma unroll
             for (int v = 6; v < 8; ++v) {

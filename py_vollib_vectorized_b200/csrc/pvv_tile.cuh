@@ -82,7 +82,7 @@ struct PriceItems {
 
 // _model_calls.py:70-78 up to the call of normalised_black: intrinsic, put-call parity flip,
 // x = ln(F/K) oriented for the out-of-the-money twin, sqrt(F) sqrt(K).
-template <int T>
+template <bool BOUNDED, int T>
 __device__ __forceinline__ void stage_price_item(PriceItems<T> &it, int item, double flag, double F, double K, double sqrtK, double s,
                                                  double deflater, unsigned &st) {
     const double payoff = flag < 0 ? K - F : F - K;
@@ -90,10 +90,10 @@ __device__ __forceinline__ void stage_price_item(PriceItems<T> &it, int item, do
     const bool itm = flag * (F - K) > 0;
     const double qq = itm ? -flag : flag;
     if (K == 0.0) st |= ST_ZERO_DIVISION;
-    const double x = log_g(F / K);
+    const double x = log_g(div_sel<BOUNDED>(F, K));
     it.x[item] = qq < 0 ? -x : x;
     it.s[item] = s;
-    it.scale[item] = sqrt(F) * sqrtK;
+    it.scale[item] = sqrt_sel<BOUNDED>(F) * sqrtK;
     it.intr[item] = itm ? -intrinsic : intrinsic;
     it.defl[item] = deflater;
 }
