@@ -77,17 +77,17 @@ def make_chain(workload, n, seed, pricer=None):
     return chain_cfg2(n, seed=seed)
 
 
-# DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01i_ncu_full_summary.txt:
+# DP instructions (DFMA+DMUL+DADD+DSETP) per contract from the ncu captures under profiles/r01j_ncu_full_summary.txt:
 #   algorithmic = executed on ACTIVE lanes (the work the reference's formulas need; invariant under regrouping),
 #   slots       = warp-level issues x 32 / contracts (what occupies the FP64 pipe, inactive lanes included).
-DP_INST_PER_CONTRACT = {"greeks": 1839.0, "price": 254.0, "iv": 1314.0, "iv_greeks": 3131.0, "surface": 1839.0 + 254.0, "analytic": 174.0}
-DP_SLOTS_PER_CONTRACT = {"greeks": 2123.0, "price": 300.0, "iv": 1459.0, "iv_greeks": 3516.0, "surface": 2123.0 + 300.0, "analytic": 223.0}
+DP_INST_PER_CONTRACT = {"greeks": 1861.0, "price": 268.0, "iv": 1336.0, "iv_greeks": 3175.0, "surface": 1861.0 + 268.0, "analytic": 174.0}
+DP_SLOTS_PER_CONTRACT = {"greeks": 2145.0, "price": 314.0, "iv": 1479.0, "iv_greeks": 3555.0, "surface": 2145.0 + 314.0, "analytic": 223.0}
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per contract and launch, from the same ncu --set full
 # captures.  K1/K2 stay below the algorithmic bytes (the outputs of a launch are still in the 126 MB L2 when the
 # kernel ends); K3/K4 exceed them by their register-spill traffic and the second read of t (HBM is 5 % busy).
-TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 45.7, "price": 41.1, "iv": 69.7, "iv_greeks": 139.6, "analytic": 76.6, "surface": 45.7 + 41.1}
+TRAFFIC_BYTES_PER_CONTRACT = {"greeks": 46.1, "price": 41.1, "iv": 74.3, "iv_greeks": 137.4, "analytic": 76.4, "surface": 46.1 + 41.1}
 
 
 class ClockSampler:

@@ -8,7 +8,7 @@ $B > gpurun_out/${TAG}_plain_greeks.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv $B > gpurun_out/${TAG}_ncu_launches.log 2>&1
 for W in ${WL:-greeks price iv iv_greeks}; do
   N=""; K="${W}_kernel"
-  [ "$W" = "iv" ] && N="--n 2000000" && K="^iv_kernel"
+  [ "$W" = "iv" ] && N="--n 3000000" && K="^iv_kernel"
   [ "$W" = "iv_greeks" ] && N="--n 2000000"
   [ "$W" = "greeks" ] && K="^greeks_kernel"
   C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline $N"
