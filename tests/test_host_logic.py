@@ -36,6 +36,37 @@ def test_flag_encoding_matches_reference_dict():
     assert out.dtype == np.int8 and out[:4].tolist() == [1, -1, -1, 1]
 
 
+def test_flag_encoding_fast_paths_agree_with_the_dict():
+    """Every array layout has its own encoder (C passes over 4- / 8-byte cells, the Arrow data buffer, PyObject*
+    identity): all of them must give what the reference's per-element dict lookup gives, threaded or not."""
+    enc = df_._preprocess_flags
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 70_001, 2_300_000):  # the last one crosses the threading threshold of the C helpers
+        base = rng.choice(np.array([1, -1], dtype=np.int8), n)
+        chars = np.where(base > 0, 'c', 'p')
+        cases = {
+            "<U1": chars,
+            "<U1 strided": np.repeat(chars, 2)[::2],
+            "<U2": np.where(base > 0, '1', '-1'),
+            "object": chars.astype(object),
+            "int64": base.astype(np.int64), "int32": base.astype(np.int32), "int16": base.astype(np.int16),
+            "float64": base.astype(np.float64), "float32": base.astype(np.float32),
+            "arrow": pd.Series(chars, dtype="string"),
+            "arrow mixed width": pd.Series(np.where(base > 0, 'c', '-1'), dtype="string"),
+            "list": chars.tolist() if n < 100_000 else None,
+        }
+        for name, flags in cases.items():
+            if flags is None:
+                continue
+            out = enc(flags)
+            assert out.dtype == np.int8 and np.array_equal(out, base), (name, n)
+    assert enc(np.array([1, 1], dtype=np.uint32)).tolist() == [1, 1]
+    for bad in (np.array(['c', 'x', 'p']), np.array([1, 2, -1]), np.array([1.0, 0.5]), np.array([1, 3], dtype=np.uint32),
+                np.array([1, -1, 0], dtype=np.int32), pd.Series(['c', 'q'], dtype="string"), np.array([np.nan, 1.0])):
+        with pytest.raises(KeyError):
+            enc(bad)
+
+
 def test_broadcast_keeps_scalars_as_stride_zero():
     c = df_.maybe_format_data_and_broadcast(95, [100, 90], .2, pd.Series([.1, .2]), np.array([1, -1], dtype=np.int8), dtype=np.float64)
     assert c.n == 2
