@@ -143,7 +143,7 @@ PVV_API int pvv_unit_offsets(int64_t n, const void *offsets, int width, int thre
 
 /* ---- diagnostics used by the parity tests ----------------------------------------------------- */
 /* y[i] = f(x[i]) on the device; which: 0 exp, 1 log, 2 erfcx, 3 erfc, 4 norm_cdf, 5 inverse_norm_cdf,
- * 6 pow(x, 1/3) */
+ * 6 pow(x, 1/3), 7 sqrt_bounded(x), 8 div_bounded(x[i], x[i ^ 1]) (the guard-free fast paths of csrc/pvv_math.cuh; n even) */
 PVV_API int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void *stream);
 /* measured FP64 issue rate: runs a dependent DADD/DMUL (fmad off) chain, returns elapsed ms via *ms
  * for `iters` x 2 instructions per thread over `threads` threads */

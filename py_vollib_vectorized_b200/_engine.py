@@ -445,7 +445,8 @@ def iv_greeks_dev(model, n, flag, price_col, S, K, t, r, q, iv_out, status, outs
     return iv_out, status, outs
 
 
-UNARY = {"exp": 0, "log": 1, "erfcx": 2, "erfc": 3, "norm_cdf": 4, "inverse_norm_cdf": 5, "cbrt_pow": 6}
+UNARY = {"exp": 0, "log": 1, "erfcx": 2, "erfc": 3, "norm_cdf": 4, "inverse_norm_cdf": 5, "cbrt_pow": 6, "sqrt_bounded": 7,
+         "div_bounded_pairs": 8}
 
 
 def unary_dev(which, x):

@@ -587,6 +587,8 @@ __global__ void unary_kernel(int which, long long n, const double *__restrict__ 
         case 3: o = pvv::erfc_cody(v); break;
         case 4: o = pvv::norm_cdf(v); break;
         case 6: o = pvv::pow_g(v, 1. / 3.); break;
+        case 7: o = pvv::sqrt_bounded(v); break;
+        case 8: o = pvv::div_bounded(v, x[i ^ 1]); break;  // every element divided by its pair partner (n even)
         default: o = pvv::inverse_norm_cdf(v); break;
     }
     y[i] = o;

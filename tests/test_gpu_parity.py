@@ -77,6 +77,27 @@ def test_device_pow_is_the_host_libm(eng):
     assert_bit_equal(ref, y, "pow(x, 1/3)")
 
 
+def test_guard_free_division_and_sqrt_are_ieee_inside_their_bounds(eng):
+    """div_bounded / sqrt_bounded are the fast paths of nvcc's own fp64 divider and square root without the operand
+    guards (csrc/pvv_math.cuh): inside the documented bounds they must equal the correctly rounded IEEE results —
+    numpy's `/` and `sqrt` on the host — on every operand, including the edges of the bounds and hard-to-round cases."""
+    import torch
+    rng = np.random.default_rng(21)
+    m = 2_000_000
+    mag = np.exp2(rng.uniform(-300, 300, m))
+    a = np.concatenate([mag * rng.uniform(1, 2, m), rng.uniform(0.02, 200.0, m), 1.0 + rng.integers(0, 1 << 20, m) * 2.0 ** -52,
+                        [2.0 ** -300, 2.0 ** 300, 0.02, 1.0, 4.0, 2.0, 3.0, 1e-13, 2844.236833439171]])
+    a = a[: a.size // 2 * 2]
+    y = eng.unary_dev("sqrt_bounded", torch.from_numpy(a).cuda()).cpu().numpy()
+    assert_bit_equal(np.sqrt(a), y, "sqrt_bounded")
+    # pairs (numerator, denominator) and (denominator, numerator): quotients between 2^-600 and 2^600
+    signs = np.where(rng.random(a.size) < 0.5, -1.0, 1.0)
+    x = a * signs
+    q = eng.unary_dev("div_bounded_pairs", torch.from_numpy(x).cuda()).cpu().numpy()
+    partner = x.reshape(-1, 2)[:, ::-1].reshape(-1)
+    assert_bit_equal(x / partner, q, "div_bounded")
+
+
 @pytest.mark.parametrize("name", ["erfcx", "erfc", "norm_cdf", "inverse_norm_cdf"])
 def test_device_special_functions(eng, oracle, name):
     import torch
