@@ -408,7 +408,7 @@ def main():
                        "l2": f"{N_SETS} rotating input/output sets per GPU ({N_SETS * n * (bytes_in + bytes_out) / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"contracts sharded over {world} GPU(s), no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": "contracts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "how": ("price_dataframe() on a pandas frame (pageable memory, string flag column): flag encode + pinned staging + pipeline + frame assembly, wall clock" if wl == "surface" else "pvv_*_host C-ABI call on pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline, wall clock")},
+                    "steps": e2e_steps, "how": ("price_dataframe() on a pandas frame (pageable memory, string flag column): flag encode + pinned staging + pipeline + frame assembly, wall clock" if wl == "surface" else "pvv_*_host C-ABI call on pinned host buffers, wall clock: up to 1.5 Mi contracts one launch that reads and writes the host memory over PCIe (zero-copy), above that the chunked 3-stream H2D/kernel/D2H pipeline")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
