@@ -149,6 +149,10 @@ PVV_API int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void
  * for `iters` x 2 instructions per thread over `threads` threads */
 PVV_API int pvv_fp64_probe(int64_t threads, int iters, int use_fma, float *ms, void *stream);
 
+/* the same with `chains` (1, 2, 4, 8) independent chains per thread at `warps_per_sm` resident warps (multiple of 4):
+ * elapsed ms for iters x 16 DP instructions per thread over warps_per_sm x 32 threads on every SM */
+PVV_API int pvv_fp64_ilp_probe(int chains, int warps_per_sm, int iters, float *ms, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ def _load():
     lib.pvv_match_u32.argtypes = [i64, vp, i32, vp, vp, vp, i32]
     lib.pvv_unary_dev.argtypes = [i32, i64, vp, vp, vp]
     lib.pvv_fp64_probe.argtypes = [i64, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
+    if hasattr(lib, "pvv_fp64_ilp_probe"):
+        lib.pvv_fp64_ilp_probe.argtypes = [i32, i32, i32, ctypes.POINTER(ctypes.c_float), vp]
     return lib
 
 
@@ -212,7 +214,7 @@ def _stage(arrays):
         return arrays
     out = list(arrays)
     dst = {i: _pinned_empty(arrays[i].size, arrays[i].dtype) for i in todo}
-    if len(todo) == 1 or arrays[todo[0]].nbytes < (4 << 20):
+    if len(todo) == 1 or max(arrays[i].nbytes for i in todo) < (4 << 20):  # the int8 flag column comes first: look at the largest
         for i in todo:
             np.copyto(dst[i], arrays[i])
     else:
@@ -463,3 +465,10 @@ def fp64_probe(threads=148 * 2048, iters=4096, use_fma=False):
     _check(_lib.pvv_fp64_probe(threads, iters, int(use_fma), ctypes.byref(ms), _stream_ptr()))
     instr = float(threads) * iters * 16
     return instr / (ms.value * 1e-3)
+
+
+def fp64_ilp_probe(chains, warps_per_sm, iters=4096, sms=148):
+    """DP instructions/s of `chains` dependent DMUL+DADD chains per thread at `warps_per_sm` resident warps."""
+    ms = ctypes.c_float(0)
+    _check(_lib.pvv_fp64_ilp_probe(int(chains), int(warps_per_sm), int(iters), ctypes.byref(ms), _stream_ptr()))
+    return float(sms) * warps_per_sm * 32 * iters * 16 / (ms.value * 1e-3)

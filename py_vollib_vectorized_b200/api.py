@@ -30,7 +30,7 @@ _GREEKS = ("delta", "gamma", "theta", "rho", "vega")
 
 
 def get_all_greeks(flag, S, K, t, r, sigma, q=None, *, model="black_scholes", return_as="dataframe", dtype=np.float64,
-                   method="numerical"):
+                   method="numerical", fix_reference_bugs=False):
     """
     All five greeks of each contract, as specified by `model`
     ("black" uses the Black-Scholes stencil, exactly as the reference does).
@@ -51,12 +51,15 @@ def get_all_greeks(flag, S, K, t, r, sigma, q=None, *, model="black_scholes", re
         raise ValueError("`method` must be 'numerical' or 'analytical'")
     compute = _engine.greeks
     if method == "analytical":
-        if model == "black":
+        if model == "black" and not fix_reference_bugs:
             raise ValueError("Analytical greeks are available for `black_scholes` and `black_scholes_merton`")
         compute = _engine.analytic_greeks
     flag = _preprocess_flags(flag, dtype=dtype)
     c = maybe_format_data_and_broadcast(S, K, t, r, sigma, flag, dtype=dtype)
-    if model in ("black", "black_scholes"):
+    if model == "black" and fix_reference_bugs:
+        S, K, t, r, sigma, flag = c
+        greeks = compute("black_scholes_merton", c.n, flag, S, K, t, r, r, sigma)  # zero carry: q = r
+    elif model in ("black", "black_scholes"):
         S, K, t, r, sigma, flag = c
         greeks = compute(model, c.n, flag, S, K, t, r, None, sigma)
     elif model == "black_scholes_merton":

@@ -303,7 +303,7 @@ template <int NT, int IPT>
 struct IvTile {
     static constexpr int C = NT * IPT;
     double x[C], beta[C];
-    double q[4][C];             // until the guess: b_c, v_c, s_2, b_2;  afterwards: s, s_left, s_right, b
+    double q[5][C];             // until the guess: b_c, v_c, s_2, b_2, v_2;  afterwards: s, s_left, s_right, b, b'
     unsigned char run[C];       // the contract takes part in the current batch
     unsigned char mode[C];      // iteration objective (MODE_*)
     unsigned char zde[C];       // a batch evaluation divided by zero
@@ -311,14 +311,16 @@ struct IvTile {
     pvv::TileSort<NT, IPT> ts;  // order of the b(x, s) batches
     pvv::TileSort<NT, IPT> tg;  // order by solver branch: fixed from the initial guess to the end
 };
-// 56 bytes per contract: four contracts per thread fit the 227 KB of a 1024-thread CTA.  The centre node
+// 64 bytes per contract: three contracts per thread fit the 227 KB of a 1024-thread CTA.  The centre node
 // s_c = sqrt(|2x|) and b_max = exp(x/2) are recomputed where they are used (b_max only on the upper
-// branches) instead of being stored: same expressions, same bits, 16 bytes per contract less.
+// branches) instead of being stored: same expressions, same bits.  Every batch returns the normalised vega b'(x, s)
+// next to b(x, s): in the two common regions it shares the evaluator's exponential (nbc_eval_core), which saves the
+// solver four divisions and four exponentials per contract.
 
 // b(x[item], s_of(item)) -> out[item] for every running contract of the tile, in key-sorted order.
 // Entered with all writes to x / s / run visible (barrier by the caller); ends with a barrier.
 template <int NT, int IPT, class SOf>
-__device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, double *out) {
+__device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, double *out, double *out_vega) {
     const int tid = threadIdx.x;
     pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], s_of(c)) : (int)pvv::K_ZERO; });
 #pragma unroll 1
@@ -327,7 +329,9 @@ __device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, dou
         const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
         const double xi = sh.x[item], si = s_of(item);
         if (pvv::nbc_zde(region, xi, si)) sh.zde[item] = 1;
-        out[item] = pvv::nbc_eval(region, xi, si);
+        const pvv::D2 bv = pvv::nbc_eval_bv(region, xi, si);
+        out[item] = bv.a;
+        out_vega[item] = bv.b;
     }
     __syncthreads();
 }
@@ -338,24 +342,22 @@ __device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, dou
 template <int NT, int IPT>
 __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     const int tid = threadIdx.x;
-    double *b_c = sh.q[0], *v_c = sh.q[1], *s_2 = sh.q[2], *b_2 = sh.q[3];
+    double *b_c = sh.q[0], *v_c = sh.q[1], *s_2 = sh.q[2], *b_2 = sh.q[3], *v_2 = sh.q[4];
     const auto s_c = [&](int c) { return sqrt(fabs(2 * sh.x[c])); };
-    iv_tile_batch(sh, s_c, b_c);  // own slots only so far: no barrier needed before the sort
+    iv_tile_batch(sh, s_c, b_c, v_c);  // own slots only so far: no barrier needed before the sort
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const int c = j * NT + tid;
         if (!sh.run[c]) continue;
         const double x = sh.x[c], sc = s_c(c), beta = sh.beta[c], bc = b_c[c];
-        const double vc = pvv::normalised_vega(x, sc);
         const double b_max = (beta < bc) ? 0.0 : pvv::exp_g(0.5 * x);  // the lower side does not look at it
-        v_c[c] = vc;
-        s_2[c] = pvv::iv_second_node(beta, b_max, sc, bc, vc);
+        s_2[c] = pvv::iv_second_node(beta, b_max, sc, bc, v_c[c]);
     }
-    iv_tile_batch(sh, [&](int c) { return s_2[c]; }, b_2);
+    iv_tile_batch(sh, [&](int c) { return s_2[c]; }, b_2, v_2);
     // initial guess, contracts regrouped by branch.  From here on thread (j, tid) works on contract
     // tg.order[j * NT + tid]: the tile stays grouped by solver branch through the Householder passes.
     pvv::tile_sort(sh.tg, [&](int c) { return sh.run[c] ? pvv::iv_branch(sh.beta[c], b_c[c], b_2[c]) : (int)pvv::IV_DONE; });
-    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *b = sh.q[3];
+    double *s = sh.q[0], *s_left = sh.q[1], *s_right = sh.q[2], *b = sh.q[3], *bp = sh.q[4];
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.tg.order[j * NT + tid];
@@ -369,7 +371,7 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
         if (running) {
             const double x = sh.x[item];
             const double b_max = (branch == pvv::IV_HIGHEST) ? pvv::exp_g(0.5 * x) : 0.0;  // only the highest segment uses it
-            o = pvv::iv_initial_guess(branch, x, sh.beta[item], b_max, s_c(item), b_c[item], v_c[item], s_2[item], b_2[item]);
+            o = pvv::iv_initial_guess(branch, x, sh.beta[item], b_max, s_c(item), b_c[item], v_c[item], s_2[item], b_2[item], v_2[item]);
             running = pvv::iv_iteration_head(0, -DBL_MAX, o);
         }
         s[item] = o.s;  // the item's inputs are consumed: its slots become the iteration state
@@ -381,7 +383,7 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     __syncthreads();
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        iv_tile_batch(sh, [&](int c) { return s[c]; }, b);
+        iv_tile_batch(sh, [&](int c) { return s[c]; }, b, bp);
 #pragma unroll 1
         for (int j = 0; j < IPT; ++j) {
             const int item = sh.tg.order[j * NT + tid] & 0xfffu;
@@ -393,7 +395,7 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
             o.mode = sh.mode[item];
             const double x = sh.x[item];
             const double b_max = (o.mode == pvv::MODE_HIGHEST) ? pvv::exp_g(0.5 * x) : 0.0;  // only that objective uses it
-            const double ds = pvv::iv_iteration_tail(x, sh.beta[item], b_max, b[item], o);
+            const double ds = pvv::iv_iteration_tail(x, sh.beta[item], b_max, b[item], bp[item], o);
             bool running = false;
             if (it == 0) running = pvv::iv_iteration_head(1, ds, o);
             s[item] = o.s;
@@ -444,15 +446,15 @@ template <int NT, int IPT>
 __device__ __forceinline__ double iv_tile_vol(const IvTile<NT, IPT> &sh, int c, double ti, int mask_errors, unsigned &status) {
     status = sh.stat[c];
     if (sh.zde[c]) status |= pvv::ST_ZERO_DIVISION;
-    const double vol = sh.q[0][c] / sqrt(ti);
+    const double vol = pvv::div_zn(sh.q[0][c], sqrt(ti));  // s == 0 where the reference returns 0 without solving
     return (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) ? pvv::u2d(0x7ff8000000000000ull) : vol;
 }
 
-// K3 comes in two shapes: 1024 threads x 4 contracts (one CTA per SM, 4096 contracts, 224 KB of shared memory)
+// K3 comes in two shapes: 1024 threads x 3 contracts (one CTA per SM, 3072 contracts, 189 KB of shared memory)
 // for long columns, 512 threads x 3 contracts (two CTAs per SM, 1536 contracts each) for short ones, where the
 // last wave of big tiles would leave most SMs idle and a tile's latency shows (the host pipeline's 512 Ki-contract
 // chunks: 0.99 G IV/s end to end with the small shape, 0.95 with 2048-contract tiles).
-constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * 4;  // at least four full waves of big tiles
+constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * 3;  // at least four full waves of big tiles
 
 template <int MODEL, int NT, int IPT>
 __global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
@@ -479,11 +481,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const in
 }
 
 // ---- K4: implied volatility, then the greeks at the solved volatility (api.py:142-178) ------------
-// One CTA = 512 threads, 2048 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2
-// runs the K2 tile machinery eight times, 256 contracts (2048 stencil items) at a time, over the same
+// One CTA = 512 threads, 1536 contracts.  Phase 1 is K3's staged solve (sigma stays on chip); phase 2
+// runs the K2 tile machinery six times, 256 contracts (2048 stencil items) at a time, over the same
 // shared memory: all 512 threads stage (two per contract) and each evaluates 4 sorted items.
-// The contract inputs are re-read from global memory for phase 2 (L2-resident by then).
-constexpr int kIvgThreads = 512, kIvgIpt = 4;
+// The contract inputs are re-read from global memory for phase 2 (L2-resident by then on the chunked host pipeline
+// and for device-resident callers; the host entry point keeps zero-copy to short calls for that reason).
+constexpr int kIvgThreads = 512, kIvgIpt = 3;
 constexpr int kIvgTile = kIvgThreads * kIvgIpt;  // contracts per CTA
 constexpr int kIvgItems = 2048;                  // stencil items per sub-tile (4 per thread)
 constexpr int kIvgContracts = kIvgItems / 8;     // 256 contracts per sub-tile: every thread stages one half of a contract
@@ -621,6 +624,32 @@ __global__ void fp64_probe_kernel(int iters, double *out) {
     if (s == 123.456) out[0] = s;
 }
 
+// The same with CH independent chains per thread and an occupancy set by the caller (dynamic shared memory as
+// ballast): how the FP64 issue rate depends on instruction-level parallelism and on resident warps (tools/probe_ilp.py;
+// the numbers behind DESIGN.md section 5's "what does not limit the kernels").
+template <int CH>
+__global__ void fp64_ilp_probe_kernel(int iters, double *out) {
+    double a[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) a[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double m = 1.0000000001, c = 1e-12;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8 / CH; ++rep) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                a[j] = __dmul_rn(a[j], m);
+                a[j] = __dadd_rn(a[j], c);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;
+}
+
 inline int grid_tiles(long long n, int per_cta) { return (int)((n + per_cta - 1) / per_cta); }
 
 // dynamic shared memory above the 48 KB default needs the opt-in once per kernel (and per device: cheap, so every launch)
@@ -634,9 +663,9 @@ inline void launch_iv_shape(long long n, const int8_t *flag, const double *price
                             const double *r, const double *q, const Strides &st, int mask_errors, double *iv, uint8_t *status, long long *fz,
                             long long base, cudaStream_t s) {
     if (n >= kIvBigTileMin) {
-        using Tile = IvTile<1024, 4>;
-        allow_smem(iv_kernel<MODEL, 1024, 4>, sizeof(Tile));
-        iv_kernel<MODEL, 1024, 4><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        using Tile = IvTile<1024, 3>;
+        allow_smem(iv_kernel<MODEL, 1024, 3>, sizeof(Tile));
+        iv_kernel<MODEL, 1024, 3><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
     } else {
         using Tile = IvTile<512, 3>;
         allow_smem(iv_kernel<MODEL, 512, 3>, sizeof(Tile));
@@ -798,6 +827,39 @@ int pvv_fp64_probe(int64_t threads, int iters, int use_fma, float *ms, void *str
     return launch_status();
 }
 
+// chains: 1, 2, 4 or 8 dependent DMUL+DADD chains per thread (16 DP instructions per thread and iteration in every
+// case); warps_per_sm: resident warps (multiple of 4, at most 64), enforced with shared-memory ballast.
+int pvv_fp64_ilp_probe(int chains, int warps_per_sm, int iters, float *ms, void *stream) {
+    if ((chains != 1 && chains != 2 && chains != 4 && chains != 8) || warps_per_sm < 4 || warps_per_sm > 64 || warps_per_sm % 4) return PVV_E_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, 8);
+    if (e != cudaSuccess) return (int)e;
+    const int block = 128;  // 4 warps: one per scheduler
+    const int ctas_per_sm = warps_per_sm / 4;
+    const size_t ballast = (size_t)(227 * 1024) / ctas_per_sm - 1024 - 256;  // leaves no room for one more CTA
+    void (*k)(int, double *) = chains == 1 ? fp64_ilp_probe_kernel<1> : chains == 2 ? fp64_ilp_probe_kernel<2> : chains == 4 ? fp64_ilp_probe_kernel<4> : fp64_ilp_probe_kernel<8>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ballast);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(a, s);
+        k<<<sms * ctas_per_sm, block, ballast, s>>>(iters, out);
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+    }
+    g_launches += 2;
+    cudaEventElapsedTime(ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    return launch_status();
+}
+
 // -------------------------------------------------------------------------------------------------
 // Host-buffer pipeline: chunks of `chunk` contracts round-robin over `nstreams` streams; each stream
 // owns one device slot (inputs + outputs).  H2D(k+1), kernel(k) and D2H(k-1) overlap across streams
@@ -843,6 +905,20 @@ inline SlotView view(const pvv_ctx *c, int i) {
     do {                                  \
         cudaError_t e_ = (call);          \
         if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+// Error exit of the pipeline: copies and kernels already enqueued keep writing into the caller's arrays and the ctx
+// slots, so every stream is drained before the code is handed back (secondary errors ignored, sticky error cleared).
+inline int pipeline_fail(pvv_ctx *c, int code) {
+    for (int i = 0; i < c->nstreams; ++i)
+        if (c->stream[i]) cudaStreamSynchronize(c->stream[i]);
+    cudaGetLastError();
+    return code;
+}
+#define PVV_CKP(call)                                            \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return pipeline_fail(c, (int)e_); \
     } while (0)
 
 // out[i] = vals[j] where in[i] == keys[j], else 0; returns the number of unmatched cells.  The keys live in
@@ -925,6 +1001,16 @@ inline long long zero_copy_max() {
     }();
     return v;
 }
+// K4 reads its inputs three times (the solve, then both staging halves of the greeks phase): from device memory the
+// repeats hit the L2, over a zero-copy mapping each one is another PCIe read.  Zero-copy therefore only serves its
+// latency-bound short calls; PVV_ZERO_COPY_MAX_IVG overrides (tools/probe_zc_threshold.py measures the crossover).
+inline long long zero_copy_max_iv_greeks() {
+    static const long long v = [] {
+        const char *e = getenv("PVV_ZERO_COPY_MAX_IVG");
+        return e ? atoll(e) : (1ll << 17);
+    }();
+    return v < zero_copy_max() ? v : zero_copy_max();
+}
 
 // Shared driver of the four host entry points.
 //   in[k]/in_stride[k]: host double columns (k < n_in), flag/flag_stride: host int8 column
@@ -932,24 +1018,25 @@ inline long long zero_copy_max() {
 //   launch(slotview, dev_in[], dev_flag, strides, n_chunk, stream): enqueues the kernel
 template <class Launch>
 int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_stride, int n_in, const double *const *in,
-                 const long long *in_stride, int n_out, double *const *out, uint8_t *status, int64_t *first_zde, Launch launch) {
+                 const long long *in_stride, int n_out, double *const *out, uint8_t *status, int64_t *first_zde, Launch launch,
+                 long long zc_max = -1) {
     PVV_CK(cudaSetDevice(c->device));
     const long long big = LLONG_MAX;
-    PVV_CK(cudaMemcpyAsync(c->first_zde, &big, 8, cudaMemcpyHostToDevice, c->stream[0]));
+    PVV_CKP(cudaMemcpyAsync(c->first_zde, &big, 8, cudaMemcpyHostToDevice, c->stream[0]));
     // broadcast scalars: one upload
     double hs[8] = {0};
     for (int k = 0; k < n_in; ++k)
         if (in_stride[k] == 0 && in[k]) hs[k] = in[k][0];
-    PVV_CK(cudaMemcpyAsync(c->scalars, hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream[0]));
+    PVV_CKP(cudaMemcpyAsync(c->scalars, hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream[0]));
     int8_t hf[8] = {0};
     if (flag_stride == 0) hf[0] = flag[0];
-    PVV_CK(cudaMemcpyAsync((char *)c->scalars + 64, hf, 8, cudaMemcpyHostToDevice, c->stream[0]));
-    PVV_CK(cudaStreamSynchronize(c->stream[0]));
+    PVV_CKP(cudaMemcpyAsync((char *)c->scalars + 64, hf, 8, cudaMemcpyHostToDevice, c->stream[0]));
+    PVV_CKP(cudaStreamSynchronize(c->stream[0]));
     // Short calls on pinned buffers: ONE launch straight on the host memory (UVA zero-copy).  Reads and
     // writes stream over PCIe in both directions while the SMs compute, with no per-chunk copy latency:
     // measured 1.22 ms vs 1.44 ms for 1 M price+greeks contracts; the chunked DMA pipeline wins again
     // from a few million contracts on (tools/probe_zerocopy.py).
-    if (n <= zero_copy_max()) {
+    if (n <= (zc_max >= 0 ? zc_max : zero_copy_max())) {
         bool ok = true;
         SlotView z{};
         const double *zin[kInCols] = {nullptr};
@@ -965,10 +1052,10 @@ int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_str
         if (status && ok) ok = (z.status = (uint8_t *)mapped_pointer(status)) != nullptr;
         if (ok) {
             int rc = launch(z, zin, zflag, n, 0, c->stream[0]);
-            if (rc != 0) return rc;
+            if (rc != 0) return pipeline_fail(c, rc);
             long long fz0 = big;
-            PVV_CK(cudaMemcpyAsync(&fz0, c->first_zde, 8, cudaMemcpyDeviceToHost, c->stream[0]));
-            PVV_CK(cudaStreamSynchronize(c->stream[0]));
+            PVV_CKP(cudaMemcpyAsync(&fz0, c->first_zde, 8, cudaMemcpyDeviceToHost, c->stream[0]));
+            PVV_CKP(cudaStreamSynchronize(c->stream[0]));
             if (first_zde) *first_zde = (fz0 == big) ? -1 : fz0;
             return 0;
         }
@@ -993,25 +1080,25 @@ int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_str
             if (!in[j]) { dev_in[j] = nullptr; continue; }
             if (in_stride[j] == 0) dev_in[j] = c->scalars + j;
             else {
-                PVV_CK(cudaMemcpyAsync(v.in[j], in[j] + off, 8 * m, cudaMemcpyHostToDevice, s));
+                PVV_CKP(cudaMemcpyAsync(v.in[j], in[j] + off, 8 * m, cudaMemcpyHostToDevice, s));
                 dev_in[j] = v.in[j];
             }
         }
         const int8_t *dev_flag;
         if (flag_stride == 0) dev_flag = (const int8_t *)((char *)c->scalars + 64);
         else {
-            PVV_CK(cudaMemcpyAsync(v.flag, flag + off, m, cudaMemcpyHostToDevice, s));
+            PVV_CKP(cudaMemcpyAsync(v.flag, flag + off, m, cudaMemcpyHostToDevice, s));
             dev_flag = v.flag;
         }
         int rc = launch(v, dev_in, dev_flag, m, off, s);
-        if (rc != 0) return rc;
+        if (rc != 0) return pipeline_fail(c, rc);
         for (int j = 0; j < n_out; ++j)
-            if (out[j]) PVV_CK(cudaMemcpyAsync(out[j] + off, v.out[j], 8 * m, cudaMemcpyDeviceToHost, s));
-        if (status) PVV_CK(cudaMemcpyAsync(status + off, v.status, m, cudaMemcpyDeviceToHost, s));
+            if (out[j]) PVV_CKP(cudaMemcpyAsync(out[j] + off, v.out[j], 8 * m, cudaMemcpyDeviceToHost, s));
+        if (status) PVV_CKP(cudaMemcpyAsync(status + off, v.status, m, cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < c->nstreams; ++i) PVV_CK(cudaStreamSynchronize(c->stream[i]));
+    for (int i = 0; i < c->nstreams; ++i) PVV_CKP(cudaStreamSynchronize(c->stream[i]));
     long long fz = big;
-    PVV_CK(cudaMemcpy(&fz, c->first_zde, 8, cudaMemcpyDeviceToHost));
+    PVV_CKP(cudaMemcpy(&fz, c->first_zde, 8, cudaMemcpyDeviceToHost));
     if (first_zde) *first_zde = (fz == big) ? -1 : fz;
     return 0;
 }
@@ -1121,7 +1208,8 @@ int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, c
                                                     v.status, delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr,
                                                     theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
                                                     (int64_t *)ctx->first_zde, off, s);
-                        });
+                        },
+                        zero_copy_max_iv_greeks());
 }
 
 int pvv_analytic_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t,

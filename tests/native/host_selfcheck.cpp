@@ -16,6 +16,11 @@ X double pvvh_pow(double x, double y) { return pvv::pow_g(x, y); }
 X void pvvh_pow_array(long n, const double *x, double y, double *out) { for (long i = 0; i < n; ++i) out[i] = pvv::pow_g(x[i], y); }
 X void pvvh_exp_array(long n, const double *x, double *y) { for (long i = 0; i < n; ++i) y[i] = pvv::exp_g(x[i]); }
 X void pvvh_log_array(long n, const double *x, double *y) { for (long i = 0; i < n; ++i) y[i] = pvv::log_g(x[i]); }
+// x / c through the zero-safe constant division of pvv_math.cuh (c = 6: Householder factor; c = Cody's B[3])
+X void pvvh_div_const_array(long n, const double *x, double c, double *y) {
+    const double rc = 1.0 / c;
+    for (long i = 0; i < n; ++i) y[i] = pvv::div_by_const_zn(x[i], c, rc);
+}
 X double pvvh_const(int which) {
     switch (which) {
         case 0: return PVV_SQRT_EPS;

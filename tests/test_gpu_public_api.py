@@ -228,3 +228,34 @@ def test_pricing_edge_cases(pvv):
     g = pvv.get_all_greeks(['c', 'p', 'c', 'p'], [100., 100., 110., 110.], 100., 0.0, .05, .2, return_as="dict")
     assert g["delta"].tolist() == [0.5, -0.5, 1.0, 0.0] and np.isinf(g["gamma"][:2]).all() and g["gamma"][2:].tolist() == [0.0, 0.0]
     assert g["rho"].tolist() == [0.0] * 4 and g["vega"].tolist() == [0.0] * 4
+
+
+def test_scalar_q_broadcast_and_reference_bug_fixes(pvv, oracle):
+    """Scalar q with vector inputs: rho raises like the reference (greeks.py:240-242), the other four greeks broadcast
+    it.  fix_reference_bugs=True: rho broadcasts too, and model='black' differentiates the discounted Black-76 price
+    (= the Black-Scholes-Merton stencil at zero carry), here checked against the oracle's BSM greeks with q = r."""
+    fl, S, K, t, r, sg = ['c', 'p', 'c'], 95.0, [100.0, 90.0, 95.0], .2, .05, [.2, .3, .25]
+    n = 3
+    f8 = np.array([1, -1, 1], dtype=np.int8)
+    full = lambda v: np.full(n, v) if np.isscalar(v) else np.asarray(v, dtype=np.float64)  # noqa: E731
+    ref, _ = oracle.greeks("black_scholes_merton", f8, full(S), full(K), full(t), full(r), full(sg), full(0.01))
+    fns = {"delta": pvv.vectorized_delta, "theta": pvv.vectorized_theta, "vega": pvv.vectorized_vega, "gamma": pvv.vectorized_gamma}
+    for name, fn in fns.items():
+        got = fn(fl, S, K, t, r, sg, q=0.01, model="black_scholes_merton", return_as="numpy")
+        assert_bit_equal(ref[name], got, name)
+    with pytest.raises(ValueError, match="same number of elements"):
+        pvv.vectorized_rho(fl, S, K, t, r, sg, q=0.01, model="black_scholes_merton")
+    got = pvv.vectorized_rho(fl, S, K, t, r, sg, q=0.01, model="black_scholes_merton", return_as="numpy", fix_reference_bugs=True)
+    assert_bit_equal(ref["rho"], got, "rho (fixed)")
+    # Black-76, fixed: zero carry
+    ref0, _ = oracle.greeks("black_scholes_merton", f8, full(S), full(K), full(t), full(r), full(sg), full(r))
+    allg = pvv.get_all_greeks(fl, S, K, t, r, sg, model="black", return_as="dict", fix_reference_bugs=True)
+    for name in ("delta", "gamma", "theta", "rho", "vega"):
+        assert_bit_equal(ref0[name], allg[name], "black " + name)
+        one = getattr(pvv, "vectorized_" + name)(fl, S, K, t, r, sg, model="black", return_as="numpy", fix_reference_bugs=True)
+        assert_bit_equal(ref0[name], one, "black " + name)
+    # sanity: the discounted Black-76 rho is -t * price (py_vollib.black.greeks.analytical.rho, per point: / 100)
+    price = np.exp(-r * t) * pvv.vectorized_black(fl, S, K, t, r, sg, return_as="numpy")
+    assert np.allclose(allg["rho"], -t * price * 0.01, rtol=1e-4)
+    with pytest.raises(TypeError):
+        pvv.vectorized_delta(fl, S, K, t, r, sg, model="black")

@@ -165,3 +165,28 @@ def test_argument_validation_happens_before_any_kernel():
         pvv.price_dataframe(df, **kw, sigma_col="IV", model="black_scholes_merton")
     with pytest.raises(ValueError, match="must be a string"):
         pvv.price_dataframe(df, **dict(kw, strike_col=3), sigma_col="IV")
+
+
+def test_scalar_q_with_vector_inputs_like_the_reference():
+    """greeks.py:54-56, 117, 178, 301 re-broadcast q for delta / theta / vega / gamma; only rho (greeks.py:240-242)
+    checks the length of q against r and raises.  Without a GPU the four working greeks get as far as the kernel call."""
+    from py_vollib_vectorized_b200 import _engine
+    args = (['c', 'p'], 95, [100, 90], .2, .2, .2)
+    with pytest.raises(ValueError, match="same number of elements"):
+        pvv.vectorized_rho(*args, q=0.0, model="black_scholes_merton")
+    for fn in (pvv.vectorized_delta, pvv.vectorized_theta, pvv.vectorized_vega, pvv.vectorized_gamma):
+        try:
+            out = fn(*args, q=0.0, model="black_scholes_merton", return_as="numpy")
+            assert out.shape == (2,)
+        except _engine.PvvError:
+            pass  # no CUDA device in the CPU tier: the arguments were accepted
+    try:  # the opt-in fix makes rho broadcast q too
+        assert pvv.vectorized_rho(*args, q=0.0, model="black_scholes_merton", return_as="numpy", fix_reference_bugs=True).shape == (2,)
+    except _engine.PvvError:
+        pass
+    with pytest.raises(TypeError):
+        pvv.vectorized_delta(*args, model="black")
+    try:
+        assert pvv.vectorized_delta(*args, model="black", return_as="numpy", fix_reference_bugs=True).shape == (2,)
+    except _engine.PvvError:
+        pass

@@ -84,3 +84,24 @@ def test_iv_bit_identical_to_reference(H, golden, on_error):
         # on the host pow() is glibc's too, so even the lowest branch is bit-identical
         assert_bit_equal(g[f"iv_{tag}_{on_error}_glibc"], iv, f"cfg3 IV {tag} {on_error}")
         assert set(np.unique(br)) >= {1, 2, 3}
+
+
+@pytest.mark.parametrize("c", [6.0, 2844.23683343917062])
+def test_zero_safe_constant_division_is_the_ieee_quotient(H, c):
+    """div_by_const_zn (Householder's / 6, Cody's small-argument quotient) must return the correctly rounded x / c
+    for every x: Markstein's three operations in the ordinary range, the zero itself for +-0, the divider elsewhere."""
+    rng = np.random.default_rng(17)
+    n = 4_000_000
+    mant = rng.uniform(1.0, 2.0, n)
+    x = np.concatenate([mant * 2.0 ** rng.integers(-1074, 1023, n), mant[:n // 4] * 2.0 ** rng.integers(-60, 10, n // 4),
+                        # quotients next to a rounding boundary: c * (k + 1/2 ulp) patterns
+                        c * (rng.integers(1, 2 ** 52, n // 4).astype(np.float64) * 2.0 ** -52 + 1.0) * (1 + rng.integers(-2, 3, n // 4) * 2.0 ** -53),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.0 ** -900, 2.0 ** 900, 1.7976931348623157e308]])
+    x = np.ascontiguousarray(np.concatenate([x, -x]))
+    y = np.empty_like(x)
+    H.pvvh_div_const_array.argtypes = [ctypes.c_long, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    H.pvvh_div_const_array(x.size, P(x), c, P(y))
+    with np.errstate(all="ignore"):
+        ref = x / c
+    assert_bit_equal(ref, y, f"x / {c}")
+    assert np.array_equal(np.signbit(ref), np.signbit(y))  # -0 / c = -0

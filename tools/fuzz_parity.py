@@ -28,7 +28,7 @@ def ext(rng, n, lo, hi, zero=0.01):
 total_bad = 0
 for seed, (lo, hi) in enumerate([(-300, 300), (-30, 30), (-5, 5), (-320, -280), (280, 308)]):
     rng = np.random.default_rng(seed)
-    n = 1_000_000
+    n = int(os.environ.get("FUZZ_N", "1000000"))
     S, K = ext(rng, n, lo, hi), ext(rng, n, lo, hi)
     if seed == 2:
         K = S * np.exp(rng.normal(0, 0.5, n))

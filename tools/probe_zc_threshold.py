@@ -2,7 +2,7 @@ import os, sys, time, subprocess
 import numpy as np
 if len(sys.argv) == 1:
     for zc in ("0", "100000000"):
-        subprocess.run([sys.executable, __file__, zc], env=dict(os.environ, PVV_ZERO_COPY_MAX=zc))
+        subprocess.run([sys.executable, __file__, zc], env=dict(os.environ, PVV_ZERO_COPY_MAX=zc, PVV_ZERO_COPY_MAX_IVG=zc))
     sys.exit(0)
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,6 +17,8 @@ for n in (100_000, 500_000, 1_000_000, 2_000_000, 4_000_000, 8_000_000):
     price = E.price("black_scholes", n, col("flag"), col("S"), col("K"), col("t"), col("r"), None, col("sigma"))
     ivo = pin(np.empty(n)); st = pin(np.empty(n, dtype=np.uint8)); hp = pin(price)
     fs = {"greeks": lambda: E.greeks("black_scholes", n, col("flag"), col("S"), col("K"), col("t"), col("r"), None, col("sigma"), with_price=True, outs=on),
+          "iv_greeks": lambda: E.iv_greeks("black_scholes", n, col("flag"), (hp, 1), col("S"), col("K"), col("t"), col("r"), None, status=st,
+                                           outs={k: (ivo if k == "iv" else on[k]) for k in ("iv",) + E.GREEK_NAMES}),
           "iv": lambda: E.iv("black_scholes", n, col("flag"), (hp, 1), col("S"), col("K"), col("t"), col("r"), None, out=ivo, status=st)}
     for name, f in fs.items():
         for _ in range(3): f()

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): one ncu --set full capture per (variant, workload).
+#   VARIANTS="base nopair" WL="greeks iv" TAG=r02b bash tools/profile_variants.sh
+mkdir -p gpurun_out
+TAG=${TAG:-prof}
+for V in ${VARIANTS:-main}; do
+  if [ "$V" = "main" ]; then unset PVV_LIB; else export PVV_LIB=$PWD/py_vollib_vectorized_b200/build/libpvv_$V.so; fi
+  for W in ${WL:-greeks iv}; do
+    N=""; K="${W}_kernel"
+    [ "$W" = "iv" ] && N="--n 3000000" && K="^iv_kernel"
+    [ "$W" = "iv_greeks" ] && N="--n 2000000"
+    [ "$W" = "greeks" ] && K="^greeks_kernel"
+    [ "$W" = "analytic" ] && N="--n 4000000" && K="analytic_kernel"
+    C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline $N"
+    ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/${TAG}_${V}_$W -f $C > gpurun_out/${TAG}_${V}_${W}_ncu.log 2>&1
+    tail -2 gpurun_out/${TAG}_${V}_${W}_ncu.log
+  done
+done
+ls -la gpurun_out | grep $TAG
