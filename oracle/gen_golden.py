@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE.  Needs /root/reference and numba, so it only runs in the bu
 the fixtures it writes are committed and are what travels to the GPU box.
 
     python oracle/gen_golden.py            # writes tests/golden/{cfg1_json,fake_data,cfg2,cfg3,wide,edge,kat}.npz
+    python oracle/gen_golden.py composed   # only (re)writes the price_dataframe fixtures into cfg3.npz / cfg2.npz
 
 Two flavours of the reference's public IV API are recorded (see oracle/validate_oracle.py):
   *_glibc  numpy dispatching np.exp to glibc (NPY_DISABLE_CPU_FEATURES=AVX512*): CPU-independent,
@@ -23,14 +24,17 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(ROOT, "tests", "golden")
 N = 4096
 
-if len(sys.argv) == 1:
+if len(sys.argv) == 1 or sys.argv[1] == "composed":
     # driver: run the two numpy flavours in fresh interpreters (CPU features are fixed at import)
     env = dict(os.environ, NUMBA_CACHE_DIR=os.environ.get("NUMBA_CACHE_DIR", "/tmp/nbcache"))
-    subprocess.run([sys.executable, __file__, "simd"], check=True, env=env)
-    subprocess.run([sys.executable, __file__, "glibc"], check=True, env=dict(env, NPY_DISABLE_CPU_FEATURES=_AVX512))
+    pre = "composed_" if len(sys.argv) > 1 else ""
+    subprocess.run([sys.executable, __file__, pre + "simd"], check=True, env=env)
+    subprocess.run([sys.executable, __file__, pre + "glibc"], check=True, env=dict(env, NPY_DISABLE_CPU_FEATURES=_AVX512))
     sys.exit(0)
 
 flavour = sys.argv[1]
+composed_only = flavour.startswith("composed_")
+flavour = flavour.replace("composed_", "")
 sys.path[:0] = [os.path.join(HERE, "shim"), "/root/reference", ROOT]
 sys.dont_write_bytecode = True
 
@@ -91,6 +95,37 @@ def save(name, **arrays):
 
 inputs = ("flag", "S", "K", "t", "r", "sigma", "q")
 
+
+def composed():
+    """The composed public paths (api.py:19-181): price_dataframe(price_col=...) = public IV, then get_all_greeks at that
+    IV (NaN-sigma rows of masked contracts included), for the three models on the cfg3 rows; and
+    price_dataframe(sigma_col=...) for black_scholes_merton and black on the cfg2 rows.  The IV leg goes through numpy's
+    np.exp, so the price_col fixtures exist in both flavours; the sigma_col ones are numba only."""
+    c3 = dict(np.load(os.path.join(OUT, "cfg3.npz")))
+    df = pd.DataFrame({"Flag": np.where(c3["flag"] > 0, "c", "p"), "S": c3["S"], "K": c3["K"], "T": c3["t"], "R": c3["r"], "Q": c3["q"], "Px": c3["price"]})
+    kw = dict(flag_col="Flag", underlying_price_col="S", strike_col="K", annualized_tte_col="T", riskfree_rate_col="R")
+    for model, tag in (("black_scholes_merton", "bsm"), ("black_scholes", "bs"), ("black", "black")):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with np.errstate(all="ignore"):
+                res = ref.price_dataframe(df, **kw, price_col="Px", model=model, inplace=False,
+                                          **(dict(dividend_col="Q") if model == "black_scholes_merton" else {}))
+        assert list(res.columns) == ["IV", "delta", "gamma", "theta", "rho", "vega"], list(res.columns)
+        save("cfg3", **{f"pdf_{tag}_{col}_{flavour}": res[col].values.astype(np.float64) for col in res.columns})
+    if flavour == "glibc":
+        c2 = dict(np.load(os.path.join(OUT, "cfg2.npz")))
+        df2 = pd.DataFrame({"Flag": np.where(c2["flag"] > 0, "c", "p"), "S": c2["S"], "K": c2["K"], "T": c2["t"], "R": c2["r"], "Q": c2["q"], "IV": c2["sigma"]})
+        for model, tag in (("black_scholes_merton", "bsm"), ("black", "black"), ("black_scholes", "bs")):
+            res = ref.price_dataframe(df2, **kw, sigma_col="IV", model=model, inplace=False,
+                                      **(dict(dividend_col="Q") if model == "black_scholes_merton" else {}))
+            assert list(res.columns) == ["Price", "delta", "gamma", "theta", "rho", "vega"], list(res.columns)
+            save("cfg2", **{f"pdf_{tag}_{col}": res[col].values.astype(np.float64) for col in res.columns})
+
+
+if composed_only:
+    composed()
+    sys.exit(0)
+
 if flavour == "simd":
     for f in ("cfg1_json", "fake_data", "cfg2", "cfg3", "wide", "edge", "kat"):
         p = os.path.join(OUT, f + ".npz")
@@ -147,6 +182,8 @@ c1 = dict(np.load(os.path.join(OUT, "cfg1_json.npz")))
 for tag, fl in (("c", 1), ("p", -1)):
     c = dict(flag=np.full(c1["S"].size, fl, dtype=np.int8), S=c1["S"], K=c1["K"], t=c1["t"], r=c1["R"], q=np.zeros(c1["S"].size))
     save("cfg1_json", **{f"ref_{tag}_ivroundtrip_{flavour}": public_iv(c, c1[f"ref_{tag}_price_bs"], "black_scholes", "warn")})
+
+composed()
 
 if flavour == "glibc":
     # ---- docstring known answers and SURVEY Appendix D, recomputed from the reference ---------------

@@ -344,12 +344,16 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     const int tid = threadIdx.x;
     double *b_c = sh.q[0], *v_c = sh.q[1], *s_2 = sh.q[2], *b_2 = sh.q[3], *v_2 = sh.q[4];
     const auto s_c = [&](int c) { return sqrt(fabs(2 * sh.x[c])); };
-    iv_tile_batch(sh, s_c, b_c, v_c);  // own slots only so far: no barrier needed before the sort
+    // the centre node is computed once per contract into the (still unused) s_2 slot: the sort key, the evaluation and
+    // the second node read it from there; the guess, which runs after s_2 has replaced it, computes it again
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) s_2[j * NT + tid] = s_c(j * NT + tid);
+    iv_tile_batch(sh, [&](int c) { return s_2[c]; }, b_c, v_c);  // own slots only so far: no barrier needed before the sort
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const int c = j * NT + tid;
         if (!sh.run[c]) continue;
-        const double x = sh.x[c], sc = s_c(c), beta = sh.beta[c], bc = b_c[c];
+        const double x = sh.x[c], sc = s_2[c], beta = sh.beta[c], bc = b_c[c];
         const double b_max = (beta < bc) ? 0.0 : pvv::exp_g(0.5 * x);  // the lower side does not look at it
         s_2[c] = pvv::iv_second_node(beta, b_max, sc, bc, v_c[c]);
     }
@@ -454,10 +458,14 @@ __device__ __forceinline__ double iv_tile_vol(const IvTile<NT, IPT> &sh, int c, 
 // for long columns, 512 threads x 3 contracts (two CTAs per SM, 1536 contracts each) for short ones, where the
 // last wave of big tiles would leave most SMs idle and a tile's latency shows (the host pipeline's 512 Ki-contract
 // chunks: 0.99 G IV/s end to end with the small shape, 0.95 with 2048-contract tiles).
-constexpr long long kIvBigTileMin = 4ll * 148 * 1024 * 3;  // at least four full waves of big tiles
+#ifndef PVV_IV_NT
+#define PVV_IV_NT 1024
+#define PVV_IV_IPT 3
+#endif
+constexpr long long kIvBigTileMin = 4ll * 148 * PVV_IV_NT * PVV_IV_IPT;  // at least four full waves of big tiles
 
 template <int MODEL, int NT, int IPT>
-__global__ void __launch_bounds__(NT, 1024 / NT) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
+__global__ void __launch_bounds__(NT, (NT > 512 ? 1 : 1024 / NT)) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
                                                            const double *__restrict__ S, const double *__restrict__ K,
                                                            const double *__restrict__ t, const double *__restrict__ r,
                                                            const double *__restrict__ q, Strides st, int mask_errors,
@@ -663,9 +671,9 @@ inline void launch_iv_shape(long long n, const int8_t *flag, const double *price
                             const double *r, const double *q, const Strides &st, int mask_errors, double *iv, uint8_t *status, long long *fz,
                             long long base, cudaStream_t s) {
     if (n >= kIvBigTileMin) {
-        using Tile = IvTile<1024, 3>;
-        allow_smem(iv_kernel<MODEL, 1024, 3>, sizeof(Tile));
-        iv_kernel<MODEL, 1024, 3><<<grid_tiles(n, Tile::C), 1024, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        using Tile = IvTile<PVV_IV_NT, PVV_IV_IPT>;
+        allow_smem(iv_kernel<MODEL, PVV_IV_NT, PVV_IV_IPT>, sizeof(Tile));
+        iv_kernel<MODEL, PVV_IV_NT, PVV_IV_IPT><<<grid_tiles(n, Tile::C), PVV_IV_NT, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
     } else {
         using Tile = IvTile<512, 3>;
         allow_smem(iv_kernel<MODEL, 512, 3>, sizeof(Tile));
