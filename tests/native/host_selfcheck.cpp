@@ -21,6 +21,12 @@ X void pvvh_div_const_array(long n, const double *x, double c, double *y) {
     const double rc = 1.0 / c;
     for (long i = 0; i < n; ++i) y[i] = pvv::div_by_const_zn(x[i], c, rc);
 }
+// region of the sort key against the reference-order classification (the key's region must be exact)
+X long pvvh_sort_key_mismatches(long n, const double *x, const double *s) {
+    long bad = 0;
+    for (long i = 0; i < n; ++i) bad += pvv::key_region(pvv::nbc_sort_key(x[i], s[i])) != pvv::nbc_classify(x[i], s[i]);
+    return bad;
+}
 X double pvvh_const(int which) {
     switch (which) {
         case 0: return PVV_SQRT_EPS;

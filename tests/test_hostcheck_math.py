@@ -105,3 +105,24 @@ def test_zero_safe_constant_division_is_the_ieee_quotient(H, c):
         ref = x / c
     assert_bit_equal(ref, y, f"x / {c}")
     assert np.array_equal(np.signbit(ref), np.signbit(y))  # -0 / c = -0
+
+
+def test_sort_key_region_is_the_exact_classification(H):
+    """The tiled kernels trust key_region(nbc_sort_key(x, s)) to be the reference's region (_model_calls.py:18-42):
+    the branch-free key must classify exactly like the chain of comparisons, also on the region boundaries."""
+    rng = np.random.default_rng(23)
+    n = 2_000_000
+    s = np.concatenate([rng.uniform(0, 0.5, n // 2), rng.uniform(0, 12.0, n // 2)])
+    x = -np.abs(rng.normal(0, 1, n)) * s * np.where(rng.random(n) < 0.2, 12.0, 1.0)
+    # points ON the thresholds: x = -10 s, s/2 = tau, x + s^2/2 = 0.85 s, and their neighbours by one ulp
+    tau = H.pvvh_const(3)
+    sb = rng.uniform(0.01, 8.0, 200000)
+    xb = np.concatenate([-10.0 * sb[:50000], 0.85 * sb[50000:100000] - 0.5 * sb[50000:100000] ** 2, sb[100000:150000] * (tau - 10.0) - 0.5 * sb[100000:150000] ** 2,
+                         -rng.uniform(0, 3, 50000)])
+    sb[150000:] = 2 * tau
+    xb = np.where(rng.random(200000) < 0.5, np.nextafter(xb, 0), np.nextafter(xb, -np.inf))
+    x = np.concatenate([x, xb, [0.0, -0.0, 1.0, -np.inf, np.inf, np.nan, -1.0, -1.0, -1.0, 5.0]])
+    s = np.concatenate([s, sb, [1.0, 0.0, 1.0, 1.0, 1.0, 1.0, 0.0, -1.0, np.nan, 0.0]])
+    x, s = np.ascontiguousarray(x), np.ascontiguousarray(s)
+    H.pvvh_sort_key_mismatches.restype = ctypes.c_long
+    assert H.pvvh_sort_key_mismatches(x.size, P(x), P(s)) == 0

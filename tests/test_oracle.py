@@ -162,3 +162,32 @@ def test_closed_form_greeks_oracle_is_pinned_by_the_reference_table(oracle, gold
         b = oracle.analytic_greeks("black_scholes_merton", np.full(n, fl, np.int8), g["S"], g["K"], g["t"], g["R"], g["v"], np.zeros(n))
         for k in a:
             assert np.array_equal(a[k], b[k])
+
+
+def test_closed_form_greeks_oracle_with_dividends_is_pinned_by_mpmath(oracle):
+    """The reference's regression table has q = 0 only: the Black-Scholes-Merton closed forms with a dividend yield are
+    pinned here by an independent 40-digit evaluation (mpmath) in py_vollib's greeks.analytical conventions
+    (theta per calendar day, vega and rho per point)."""
+    import mpmath as mp
+    from py_vollib_vectorized_b200.util.chains import chain_cfg2
+    mp.mp.dps = 40
+    c = chain_cfg2(300, seed=9)
+    c["q"] = np.where(np.arange(300) % 3 == 0, 0.0, c["q"] + 0.01 * (np.arange(300) % 7))  # q from 0 to 0.1
+    got = oracle.analytic_greeks("black_scholes_merton", c["flag"], c["S"], c["K"], c["t"], c["r"], c["sigma"], c["q"])
+    N = lambda x: mp.ncdf(x)  # noqa: E731
+    phi = lambda x: mp.npdf(x)  # noqa: E731
+    for i in range(300):
+        f, S, K, t, r, sg, q = (mp.mpf(float(c[k][i])) for k in ("flag", "S", "K", "t", "r", "sigma", "q"))
+        sq = mp.sqrt(t)
+        d1 = (mp.log(S / K) + (r - q + sg * sg / 2) * t) / (sg * sq)
+        d2 = d1 - sg * sq
+        Dq, Dr = mp.exp(-q * t), mp.exp(-r * t)
+        ref = {"price": f * (S * Dq * N(f * d1) - K * Dr * N(f * d2)), "delta": f * Dq * N(f * d1), "gamma": Dq * phi(d1) / (S * sg * sq),
+               "vega": S * Dq * phi(d1) * sq / 100,
+               "theta": (-S * Dq * phi(d1) * sg / (2 * sq) - f * r * K * Dr * N(f * d2) + f * q * S * Dq * N(f * d1)) / 365,
+               "rho": f * t * K * Dr * N(f * d2) / 100}
+        # price and theta subtract nearly equal terms: 1e-12 relative to the size of those terms, else to the value
+        scale = {"price": S * Dq * N(f * d1) + K * Dr * N(f * d2), "theta": (S * Dq * phi(d1) * sg / (2 * sq) + r * K * Dr + q * S * Dq) / 365}
+        for k, v in ref.items():
+            tol = 1e-12 * float(scale.get(k, abs(v))) + 1e-300
+            assert abs(float(got[k][i]) - float(v)) <= tol, (i, k, float(got[k][i]), float(v))
