@@ -413,9 +413,6 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
 
 // Front of the tile in natural order (contract c = j * NT + tid, coalesced loads): implied_volatility.py:48-86
 // and the first lines of the numba loop -> x, beta, the run flag and the status bits of every contract.
-#ifndef PVV_FRONT_PIPELINE
-#define PVV_FRONT_PIPELINE 0
-#endif
 template <int MODEL, int NT, int IPT>
 __device__ __forceinline__ void iv_tile_front(IvTile<NT, IPT> &sh, long long tile0, long long n, const int8_t *__restrict__ flag,
                                               const double *__restrict__ price, const double *__restrict__ S, const double *__restrict__ K,
@@ -427,46 +424,6 @@ __device__ __forceinline__ void iv_tile_front(IvTile<NT, IPT> &sh, long long til
         sh.tg.cnt[tid] = 0;
     }
     __syncthreads();
-#if PVV_FRONT_PIPELINE
-    // the loads of contract j + 1 are issued before contract j is worked on: one exposed global-memory latency per tile
-    // instead of one per contract
-    struct In {
-        double f, p, S, K, t, r, q;
-    };
-    const auto load = [&](int j) {
-        In v = {1.0, 0.0, 1.0, 1.0, 1.0, 0.0, 0.0};
-        const long long i = tile0 + j * NT + tid;
-        if (i < n) {
-            v.f = (double)flag[i * st.s[0]];
-            v.p = price[i * st.s[1]];
-            v.S = S[i * st.s[2]];
-            v.K = K[i * st.s[3]];
-            v.t = t[i * st.s[4]];
-            v.r = r[i * st.s[5]];
-            v.q = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[6]] : 0.0;
-        }
-        return v;
-    };
-    In cur = load(0);
-#pragma unroll 1
-    for (int j = 0; j < IPT; ++j) {
-        const int c = j * NT + tid;
-        const long long i = tile0 + c;
-        In nxt = cur;
-        if (j + 1 < IPT) nxt = load(j + 1);
-        unsigned status = 0;
-        pvv::IvFront fr;
-        fr.beta = 0.0;
-        fr.x = 0.0;
-        if (i < n) fr = pvv::iv_front<MODEL>(cur.f, cur.p, cur.S, cur.K, cur.t, cur.r, cur.q, status);
-        sh.x[c] = fr.x;
-        sh.beta[c] = fr.beta;
-        sh.run[c] = (i < n) && !(fr.beta <= 0);  // beta <= 0: the reference returns 0 without solving
-        sh.zde[c] = 0;
-        sh.stat[c] = (unsigned char)status;
-        cur = nxt;
-    }
-#else
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const int c = j * NT + tid;
@@ -486,7 +443,6 @@ __device__ __forceinline__ void iv_tile_front(IvTile<NT, IPT> &sh, long long til
         sh.zde[c] = 0;
         sh.stat[c] = (unsigned char)status;
     }
-#endif
 }
 
 // sigma = s / sqrt(t) with the on_error mask, and the final status byte of contract c
