@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
 // G solves/s): registers-resident state, 512 x 1: 4.30, 1024 x 1: 4.45; shared-memory state (72 B per
 // contract), 512 x 2: 4.36, 512 x 3: 5.33, 1024 x 3: 5.49, 768 x 4: 5.19, 384 x 4: 4.98, 512 x 6 (one CTA
 // per SM): 4.42; compact state (56 B), 1024 x 3: 5.60, 1024 x 4: 5.66.
+#ifndef PVV_IV_REUSE_ORDER
+#define PVV_IV_REUSE_ORDER 1
+#endif
 template <int NT, int IPT>
 struct IvTile {
     static constexpr int C = NT * IPT;
@@ -319,15 +322,19 @@ struct IvTile {
 
 // b(x[item], s_of(item)) -> out[item] for every running contract of the tile, in key-sorted order.
 // Entered with all writes to x / s / run visible (barrier by the caller); ends with a barrier.
-template <int NT, int IPT, class SOf>
+// RESORT = false reuses the order of the previous batch (the second Householder pass: s has moved by one converging
+// step, nearly every item still groups with the same neighbours) and takes each item's exact region from
+// nbc_classify instead of the sort key: one counting sort, its two barriers and the key refinement less per tile.
+template <bool RESORT = true, int NT, int IPT, class SOf>
 __device__ __forceinline__ void iv_tile_batch(IvTile<NT, IPT> &sh, SOf s_of, double *out, double *out_vega) {
     const int tid = threadIdx.x;
-    pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], s_of(c)) : (int)pvv::K_ZERO; });
+    if (RESORT) pvv::tile_sort(sh.ts, [&](int c) { return sh.run[c] ? pvv::nbc_sort_key(sh.x[c], s_of(c)) : (int)pvv::K_ZERO; });
 #pragma unroll 1
     for (int j = 0; j < IPT; ++j) {
         const unsigned e = sh.ts.order[j * NT + tid];
-        const int item = e & 0xfffu, region = pvv::key_region(e >> 12);
+        const int item = e & 0xfffu;
         const double xi = sh.x[item], si = s_of(item);
+        const int region = RESORT ? pvv::key_region(e >> 12) : (sh.run[item] ? pvv::nbc_classify(xi, si) : (int)pvv::R_ZERO);
         if (pvv::nbc_zde(region, xi, si)) sh.zde[item] = 1;
         const pvv::D2 bv = pvv::nbc_eval_bv(region, xi, si);
         out[item] = bv.a;
@@ -387,7 +394,8 @@ __device__ __forceinline__ void iv_tile_solve2(IvTile<NT, IPT> &sh) {
     __syncthreads();
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        iv_tile_batch(sh, [&](int c) { return s[c]; }, b, bp);
+        if (it == 0 || !PVV_IV_REUSE_ORDER) iv_tile_batch<true>(sh, [&](int c) { return s[c]; }, b, bp);
+        else iv_tile_batch<false>(sh, [&](int c) { return s[c]; }, b, bp);
 #pragma unroll 1
         for (int j = 0; j < IPT; ++j) {
             const int item = sh.tg.order[j * NT + tid] & 0xfffu;
