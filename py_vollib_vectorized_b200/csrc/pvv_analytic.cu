@@ -7,8 +7,11 @@
 // contract, arithmetic small enough (~230 DP instructions) to sit near the HBM roofline.  There is
 // no numba counterpart to be bit-identical with, so this translation unit is compiled WITH FMA
 // contraction and uses its own minimal-operation-count special functions:
-//   N(x) via Cody's scaled complementary error function evaluated once per |d| together with the
-//   density (N(-|d|) = phi(d) * erfcx(|d|/sqrt2) * sqrt(pi/2)), exp/log from the CUDA math library.
+//   N(-|d|) = exp(-d^2/2) erfcx(|d|/sqrt 2) / 2 with erfcx from a 100-interval table of degree-6 polynomials in
+//   t = 400 / (4 + y) (csrc/erfcx_table.cuh, generated with mpmath by tools/gen_erfcx_table.py: 1.6e-16 relative) held
+//   in shared memory — seven FMAs and no interval branch, where Cody's rational functions cost 32 dependent operations on
+//   one of three divergent paths (round 1: 223 issued vs 174 useful DP instructions per contract); exp/log from the CUDA
+//   math library.
 // Parity: against the closed-form float64 checker used by the tests (pvv_oracle_analytic_greeks),
 // 1e-12 relative (+1e-300 absolute), and against the reference's regression table columns
 // CD/CG/CT/CV/CR/PD/PG/PT/PV/PR (6 decimals) — tests/test_gpu_analytic.py.
@@ -19,6 +22,17 @@
 #include <initializer_list>
 
 #include "../../include/pvv.h"
+#include "erfcx_table.cuh"
+
+#ifndef PVV_ANALYTIC_STAGES
+#define PVV_ANALYTIC_STAGES 2
+#endif
+#ifndef PVV_ANALYTIC_RESIDENT
+#define PVV_ANALYTIC_RESIDENT 3    /* resident CTAs per SM: 80 registers per thread, no spills */
+#endif
+#ifndef PVV_ANALYTIC_CTAS_PER_SM
+#define PVV_ANALYTIC_CTAS_PER_SM (2 * PVV_ANALYTIC_RESIDENT)  /* grid: two waves of the resident CTAs */
+#endif
 
 namespace {
 
@@ -26,17 +40,18 @@ struct AStrides {
     int s[7];
 };
 
-// Cody's coefficients in __constant__ memory (a literal fp64 constant costs two UMOV per use on sm_100a:
-// 29 % of this kernel's instructions in the first profile).
-__constant__ double CA[5] = {3.1611237438705656, 113.864154151050156, 377.485237685302021, 3209.37758913846947, .185777706184603153};
-__constant__ double CB[4] = {23.6012909523441209, 244.024637934444173, 1282.61652607737228, 2844.23683343917062};
-__constant__ double CC[9] = {.564188496988670089, 8.88314979438837594, 66.1191906371416295, 298.635138197400131, 881.95222124176909,
-                             1712.04761263407058, 2051.07837782607147, 1230.33935479799725, 2.15311535474403846e-8};
-__constant__ double CD[8] = {15.7449261107098347, 117.693950891312499, 537.181101862009858, 1621.38957456669019, 3290.79923573345963,
-                             4362.61909014324716, 3439.36767414372164, 1230.33935480374942};
-__constant__ double CP[6] = {.305326634961232344, .360344899949804439, .125781726111229246, .0160837851487422766, 6.58749161529837803e-4,
-                             .0163153871373020978};
-__constant__ double CQ[5] = {2.56852019228982242, 1.87295284992346047, .527905102951428412, .0605183413124413191, .00233520497626869185};
+// erfcx table, coefficient-major in shared memory (tab[k * kTabStride + i]: the 32 lanes of a warp read the k-th coefficient of
+// 32 different intervals — consecutive intervals fall into consecutive bank pairs)
+constexpr int kTabRows = 100, kTabStride = 104;
+__device__ const double ERFCX_TAB[kTabRows * 8] = {PVV_ERFCX_TAB_VALUES};
+__device__ __forceinline__ void load_erfcx_table(double *tab) {
+    for (int j = threadIdx.x; j < kTabRows * 7; j += blockDim.x) {
+        const int i = j / 7, k = j - 7 * i;
+        tab[k * kTabStride + i] = ERFCX_TAB[i * 8 + k];
+    }
+    __syncthreads();
+}
+
 // scalar constants with a non-zero low word (two UMOV each as literals): 1/sqrt(2 pi), 1/sqrt 2, 1/sqrt(pi), 1/365, 0.01
 __constant__ double CK[5] = {0.3989422804014326779399460599343818684758586311649, 0.7071067811865475244008443621048490392848359376887,
                              0.56418958354775628695, 1.0 / 365.0, 0.01};
@@ -70,52 +85,17 @@ __device__ __forceinline__ double sqrt_nr(double t) {
     return __fma_rn(__fma_rn(-s, s, t), 0.5 * y, s);
 }
 
-// 0.5 * erfc(y) for y >= 0 as A + B * (N / D): Cody's rational Chebyshev approximations (Math. Comp. 1969),
-// FMA Horner form.  The division is left to the caller, which shares ONE reciprocal between the two calls
-// of a contract.  `e` = exp(-y^2) is supplied by the caller (it has exp(-d^2/2) at hand).
-struct ErfcParts {
-    double A, B, N, D;
-};
-__device__ __forceinline__ ErfcParts half_erfc_parts(double y, double e) {
-    ErfcParts p;
-    if (y <= 0.46875) {
-        const double ysq = y * y;
-        double xnum = CA[4] * ysq, xden = ysq;
+// erfcx(y) for y >= 0 given rinv = 1 / (4 + y): t = 400 rinv in (0, 100], interval floor(t), u in [-1, 1], degree-6 Horner.
+// y beyond 396 (interval 0) or NaN evaluates a finite polynomial that the caller multiplies by exp(-y^2) = 0 (or NaN).
+__device__ __forceinline__ double erfcx_tab(double rinv, const double *__restrict__ tab) {
+    const double t = 400.0 * rinv;
+    int i = (int)t;
+    i = i < 0 ? 0 : (i > kTabRows - 1 ? kTabRows - 1 : i);  // t == 100 (y == 0) belongs to the last interval, u = 1
+    const double u = __fma_rn(2.0, t, -(double)(2 * i + 1));
+    const double *c = tab + i;
+    double p = c[6 * kTabStride];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            xnum = (xnum + CA[i]) * ysq;
-            xden = (xden + CB[i]) * ysq;
-        }
-        p.A = 0.5;
-        p.B = -0.5 * y;
-        p.N = xnum + CA[3];
-        p.D = xden + CB[3];
-    } else if (y <= 4.0) {
-        double xnum = CC[8] * y, xden = y;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            xnum = (xnum + CC[i]) * y;
-            xden = (xden + CD[i]) * y;
-        }
-        p.A = 0.0;
-        p.B = 0.5 * e;
-        p.N = xnum + CC[7];
-        p.D = xden + CD[7];
-    } else {
-        const double ry = rcp_nr(y);
-        const double ysq = ry * ry;
-        double xnum = CP[5] * ysq, xden = ysq;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            xnum = (xnum + CP[i]) * ysq;
-            xden = (xden + CQ[i]) * ysq;
-        }
-        const double her = 0.5 * e * ry;
-        p.A = her * CK[2];
-        p.B = -her * ysq;
-        p.N = xnum + CP[4];
-        p.D = xden + CQ[4];
-    }
+    for (int k = 5; k >= 0; --k) p = __fma_rn(p, u, c[k * kTabStride]);
     return p;
 }
 
@@ -133,7 +113,8 @@ struct AnalyticOut {
 
 // One contract.  py_vollib's greeks.analytical conventions: theta per calendar day, vega and rho per point.
 template <int MODEL>
-__device__ __forceinline__ AnalyticOut analytic_one(bool call, double Si, double Ki, double ti, double ri, double qi, double sg) {
+__device__ __forceinline__ AnalyticOut analytic_one(bool call, double Si, double Ki, double ti, double ri, double qi, double sg,
+                                                    const double *__restrict__ tab) {
     const double sqt = sqrt(ti);
     const double ssqt = sg * sqt;
     const double rSs = rcp_nr(ssqt * Si);  // 1 / (S sigma sqrt t): gamma's denominator, and 1 / (sigma sqrt t) with it
@@ -150,9 +131,10 @@ __device__ __forceinline__ AnalyticOut analytic_one(bool call, double Si, double
     const double e1 = exp(-0.5 * d1 * d1);
     const double e2 = e1 * (SDq * rcp_nr(KDr));
     const double pdf1 = CK[0] * e1;
-    const ErfcParts p1 = half_erfc_parts(fabs(d1) * CK[1], e1), p2 = half_erfc_parts(fabs(d2) * CK[1], e2);
-    const double rD = rcp_nr(p1.D * p2.D);  // both denominators are positive polynomials between 2e-3 and 1e6
-    const double tail1 = __fma_rn(p1.B, p1.N * p2.D * rD, p1.A), tail2 = __fma_rn(p2.B, p2.N * p1.D * rD, p2.A);
+    // both tails from one reciprocal: 1 / (4 + y1) = (4 + y2) / ((4 + y1)(4 + y2))
+    const double w1 = __fma_rn(fabs(d1), CK[1], 4.0), w2 = __fma_rn(fabs(d2), CK[1], 4.0);
+    const double rw = rcp_nr(w1 * w2);
+    const double tail1 = 0.5 * e1 * erfcx_tab(rw * w2, tab), tail2 = 0.5 * e2 * erfcx_tab(rw * w1, tab);
     double N1, M1, N2, M2;  // N = N(d), M = N(-d)
     cdf_pair(d1, tail1, N1, M1);
     cdf_pair(d2, tail2, N2, M2);
@@ -170,51 +152,144 @@ __device__ __forceinline__ AnalyticOut analytic_one(bool call, double Si, double
 }
 
 // General form: one contract per thread, dense (stride 1) or broadcast (stride 0) columns, any alignment.
+// A grid-stride loop over a few CTAs per SM: the erfcx table is copied to shared memory once per CTA.
 template <int MODEL>
-__global__ void __launch_bounds__(256, 5) analytic_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
+__global__ void __launch_bounds__(256, PVV_ANALYTIC_RESIDENT) analytic_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                           const double *__restrict__ K, const double *__restrict__ t,
                                                           const double *__restrict__ r, const double *__restrict__ q,
                                                           const double *__restrict__ sigma, AStrides st, double *__restrict__ price,
                                                           double *__restrict__ delta, double *__restrict__ gamma, double *__restrict__ theta,
                                                           double *__restrict__ rho, double *__restrict__ vega) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const double qi = (MODEL == PVV_MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
-    const AnalyticOut o = analytic_one<MODEL>(flag[i * st.s[0]] > 0, S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], r[i * st.s[4]], qi,
-                                              sigma[i * st.s[6]]);
-    if (price) price[i] = o.price;
-    if (delta) delta[i] = o.delta;
-    if (gamma) gamma[i] = o.gamma;
-    if (vega) vega[i] = o.vega;
-    if (theta) theta[i] = o.theta;
-    if (rho) rho[i] = o.rho;
+    __shared__ double tab[7 * kTabStride];
+    load_erfcx_table(tab);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double qi = (MODEL == PVV_MODEL_BLACK_SCHOLES_MERTON) ? q[i * st.s[5]] : 0.0;
+        const AnalyticOut o = analytic_one<MODEL>(flag[i * st.s[0]] > 0, S[i * st.s[1]], K[i * st.s[2]], t[i * st.s[3]], r[i * st.s[4]], qi,
+                                                  sigma[i * st.s[6]], tab);
+        if (price) price[i] = o.price;
+        if (delta) delta[i] = o.delta;
+        if (gamma) gamma[i] = o.gamma;
+        if (vega) vega[i] = o.vega;
+        if (theta) theta[i] = o.theta;
+        if (rho) rho[i] = o.rho;
+    }
 }
 
-// Streaming form: all columns dense and 16-byte aligned, all six outputs wanted.  Two consecutive contracts per
-// thread: every column moves as one 128-bit access per thread (half the memory instructions and index
-// arithmetic, two independent dependency chains per thread).  n2 = number of contract PAIRS.
+// ---- streaming form with bulk-asynchronous loads (TMA, cp.async.bulk) ----------------------------------------------
+// A persistent CTA of 256 threads walks chunks of 512 contracts.  One elected thread issues the chunk's columns as 1-D bulk
+// copies global -> shared (one per column: 4 KB, the flag column 512 B) that complete on an mbarrier; PVV_ANALYTIC_STAGES
+// stages, so the copies of the next chunk(s) are in flight while chunk k is computed — the loads cost no registers and no issue slots of the
+// 255 other threads, and their latency is off the critical path (the register-loading form above stalls 3 warps per
+// issue on its long scoreboard).  Outputs go straight from registers to global memory as 128-bit stores.
+constexpr int kChunk = 512;  // contracts per chunk: two per thread
 template <int MODEL>
-__global__ void __launch_bounds__(256, 4) analytic_kernel_x2(long long n2, const char2 *__restrict__ flag, const double2 *__restrict__ S,
-                                                             const double2 *__restrict__ K, const double2 *__restrict__ t,
-                                                             const double2 *__restrict__ r, const double2 *__restrict__ q,
-                                                             const double2 *__restrict__ sigma, double2 *__restrict__ price,
-                                                             double2 *__restrict__ delta, double2 *__restrict__ gamma,
-                                                             double2 *__restrict__ theta, double2 *__restrict__ rho,
-                                                             double2 *__restrict__ vega) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n2) return;
-    const char2 f = flag[i];
-    const double2 Si = S[i], Ki = K[i], ti = t[i], ri = r[i], sg = sigma[i];
-    double2 qi = make_double2(0.0, 0.0);
-    if (MODEL == PVV_MODEL_BLACK_SCHOLES_MERTON) qi = q[i];
-    const AnalyticOut a = analytic_one<MODEL>(f.x > 0, Si.x, Ki.x, ti.x, ri.x, qi.x, sg.x);
-    const AnalyticOut b = analytic_one<MODEL>(f.y > 0, Si.y, Ki.y, ti.y, ri.y, qi.y, sg.y);
-    price[i] = make_double2(a.price, b.price);
-    delta[i] = make_double2(a.delta, b.delta);
-    gamma[i] = make_double2(a.gamma, b.gamma);
-    theta[i] = make_double2(a.theta, b.theta);
-    rho[i] = make_double2(a.rho, b.rho);
-    vega[i] = make_double2(a.vega, b.vega);
+struct alignas(128) AnalyticStage {
+    double2 col[(MODEL == PVV_MODEL_BLACK_SCHOLES_MERTON) ? 6 : 5][kChunk / 2];  // S, K, t, r, sigma[, q]
+    char2 flag[kChunk / 2];
+};
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256, PVV_ANALYTIC_RESIDENT) analytic_kernel_tma(long long nchunks, const int8_t *__restrict__ flag,
+                                                                                  const double *__restrict__ S, const double *__restrict__ K,
+                                                                                  const double *__restrict__ t, const double *__restrict__ r,
+                                                                                  const double *__restrict__ q, const double *__restrict__ sigma,
+                                                                                  double2 *__restrict__ price, double2 *__restrict__ delta,
+                                                                                  double2 *__restrict__ gamma, double2 *__restrict__ theta,
+                                                                                  double2 *__restrict__ rho, double2 *__restrict__ vega) {
+    constexpr bool BSM = MODEL == PVV_MODEL_BLACK_SCHOLES_MERTON;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    AnalyticStage<MODEL> *stage = reinterpret_cast<AnalyticStage<MODEL> *>(smem_raw);
+    constexpr int NS = PVV_ANALYTIC_STAGES;
+    double *tab = reinterpret_cast<double *>(smem_raw + NS * sizeof(AnalyticStage<MODEL>));
+    uint64_t *full = reinterpret_cast<uint64_t *>(tab + 7 * kTabStride);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int k = 0; k < NS; ++k) mbar_init(&full[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    load_erfcx_table(tab);  // ends with a barrier: the mbarriers are initialised for everyone
+    const auto issue = [&](int s, long long c) {  // thread 0: the columns of chunk c into stage s
+        constexpr uint32_t kBytes = (BSM ? 6u : 5u) * kChunk * 8u + kChunk;
+        mbar_expect_tx(&full[s], kBytes);
+        const long long o = c * kChunk;
+        bulk_g2s(stage[s].col[0], S + o, kChunk * 8, &full[s]);
+        bulk_g2s(stage[s].col[1], K + o, kChunk * 8, &full[s]);
+        bulk_g2s(stage[s].col[2], t + o, kChunk * 8, &full[s]);
+        bulk_g2s(stage[s].col[3], r + o, kChunk * 8, &full[s]);
+        bulk_g2s(stage[s].col[4], sigma + o, kChunk * 8, &full[s]);
+        if (BSM) bulk_g2s(stage[s].col[BSM ? 5 : 4], q + o, kChunk * 8, &full[s]);
+        bulk_g2s(stage[s].flag, flag + o, kChunk, &full[s]);
+    };
+    const long long step = gridDim.x;
+    long long c = blockIdx.x;
+    if (tid == 0) {
+        for (int k = 0; k < NS; ++k)
+            if (c + k * step < nchunks) issue(k, c + k * step);
+    }
+    int s = 0;
+    uint32_t parity = 0;
+    for (; c < nchunks; c += step) {
+        mbar_wait(&full[s], parity);
+        const double2 Si = stage[s].col[0][tid], Ki = stage[s].col[1][tid], ti = stage[s].col[2][tid], ri = stage[s].col[3][tid],
+                      sg = stage[s].col[4][tid];
+        double2 qi = make_double2(0.0, 0.0);
+        if (BSM) qi = stage[s].col[BSM ? 5 : 4][tid];
+        const char2 f = stage[s].flag[tid];
+        __syncthreads();  // every thread has read the stage: it can be refilled
+        if (tid == 0 && c + NS * step < nchunks) issue(s, c + NS * step);
+        const AnalyticOut a = analytic_one<MODEL>(f.x > 0, Si.x, Ki.x, ti.x, ri.x, qi.x, sg.x, tab);
+        const AnalyticOut b = analytic_one<MODEL>(f.y > 0, Si.y, Ki.y, ti.y, ri.y, qi.y, sg.y, tab);
+        const long long i = c * (kChunk / 2) + tid;
+        price[i] = make_double2(a.price, b.price);
+        delta[i] = make_double2(a.delta, b.delta);
+        gamma[i] = make_double2(a.gamma, b.gamma);
+        theta[i] = make_double2(a.theta, b.theta);
+        rho[i] = make_double2(a.rho, b.rho);
+        vega[i] = make_double2(a.vega, b.vega);
+        if (++s == NS) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+}
+template <int MODEL>
+constexpr size_t analytic_tma_smem() {
+    return PVV_ANALYTIC_STAGES * sizeof(AnalyticStage<MODEL>) + 7 * kTabStride * sizeof(double) + PVV_ANALYTIC_STAGES * sizeof(uint64_t);
+}
+
+// grid of a grid-stride launch: every SM gets `per_sm` CTAs (or fewer CTAs than that when the column is short)
+inline int stride_grid(long long work_items, int per_sm) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const long long need = (work_items + 255) / 256, cap = (long long)sms * per_sm;
+    return (int)(need < cap ? need : cap);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -237,28 +312,31 @@ int pvv_analytic_greeks_dev(int model, int64_t n, const int8_t *flag, const doub
     cudaStream_t s = (cudaStream_t)stream;
     const bool bsm = model == PVV_MODEL_BLACK_SCHOLES_MERTON;
     // streaming form for the bulk of a dense, aligned, all-outputs call; the general form for everything else
-    bool fast = price && delta && gamma && theta && rho && vega && n >= 2 && (reinterpret_cast<uintptr_t>(flag) & 1u) == 0;
+    bool fast = price && delta && gamma && theta && rho && vega;
     for (int i = 0; i < 7 && fast; ++i) fast = st.s[i] == 1 || (i == 5 && !bsm);
     for (const void *p : {(const void *)S, (const void *)K, (const void *)t, (const void *)r, (const void *)sigma, (const void *)price,
                           (const void *)delta, (const void *)gamma, (const void *)theta, (const void *)rho, (const void *)vega})
         fast = fast && aligned16(p);
     if (bsm) fast = fast && aligned16(q);
     long long done = 0;
-    if (fast) {
-        const long long n2 = n / 2;
-        const int grid2 = (int)((n2 + 255) / 256);
-#define PVV_X2(M)                                                                                                                      \
-    analytic_kernel_x2<M><<<grid2, 256, 0, s>>>(n2, (const char2 *)flag, (const double2 *)S, (const double2 *)K, (const double2 *)t,   \
-                                                (const double2 *)r, (const double2 *)q, (const double2 *)sigma, (double2 *)price,      \
-                                                (double2 *)delta, (double2 *)gamma, (double2 *)theta, (double2 *)rho, (double2 *)vega)
-        if (bsm) PVV_X2(PVV_MODEL_BLACK_SCHOLES_MERTON);
-        else PVV_X2(PVV_MODEL_BLACK_SCHOLES);
-#undef PVV_X2
-        done = 2 * n2;
+    if (fast && n >= kChunk && aligned16(flag)) {
+        const long long nchunks = n / kChunk;
+        const int grid = stride_grid(nchunks * 256, PVV_ANALYTIC_RESIDENT);
+#define PVV_TMA(M)                                                                                                                     \
+    do {                                                                                                                               \
+        cudaFuncSetAttribute(analytic_kernel_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analytic_tma_smem<M>());         \
+        analytic_kernel_tma<M><<<grid, 256, analytic_tma_smem<M>(), s>>>(nchunks, flag, S, K, t, r, q, sigma, (double2 *)price,        \
+                                                                         (double2 *)delta, (double2 *)gamma, (double2 *)theta,        \
+                                                                         (double2 *)rho, (double2 *)vega);                             \
+    } while (0)
+        if (bsm) PVV_TMA(PVV_MODEL_BLACK_SCHOLES_MERTON);
+        else PVV_TMA(PVV_MODEL_BLACK_SCHOLES);
+#undef PVV_TMA
+        done = nchunks * kChunk;
     }
-    if (done < n) {  // the odd last contract of the streaming form, or the whole call
+    if (done < n) {  // the last partial chunk of the streaming form, or the whole call
         const long long m = n - done;
-        const int grid = (int)((m + 255) / 256);
+        const int grid = stride_grid(m, PVV_ANALYTIC_CTAS_PER_SM);
         const double *qq = q ? q + done * st.s[5] : q;
 #define PVV_X1(M)                                                                                                                          \
     analytic_kernel<M><<<grid, 256, 0, s>>>(m, flag + done * st.s[0], S + done * st.s[1], K + done * st.s[2], t + done * st.s[3],           \

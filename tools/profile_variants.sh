@@ -10,7 +10,7 @@ for V in ${VARIANTS:-main}; do
     [ "$W" = "iv" ] && N="--n 3000000" && K="^iv_kernel"
     [ "$W" = "iv_greeks" ] && N="--n 2000000"
     [ "$W" = "greeks" ] && K="^greeks_kernel"
-    [ "$W" = "analytic" ] && N="--n 4000000" && K="analytic_kernel"
+    [ "$W" = "analytic" ] && N="--n 4000000" && K="analytic_kernel_tma"
     C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline $N"
     ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/${TAG}_${V}_$W -f $C > gpurun_out/${TAG}_${V}_${W}_ncu.log 2>&1
     tail -2 gpurun_out/${TAG}_${V}_${W}_ncu.log
