@@ -244,7 +244,9 @@ __device__ __forceinline__ void finish_greeks(const pvv::PriceItems<T> &items, i
     if (vega) vega[i] = (p[6] - p[7]) / 2.;
 }
 
-template <int MODEL>
+// FULL: every column dense and all six outputs wanted (get_all_greeks / price_dataframe): the stride multiplications, the
+// want / need bit tests of the staging loop and the null checks of the stores are compiled out.
+template <int MODEL, bool FULL>
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                                  const double *__restrict__ K, const double *__restrict__ t,
                                                                  const double *__restrict__ r, const double *__restrict__ q,
@@ -261,21 +263,32 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
     const int c = tid % kGreekContracts;     // contract within the tile
     const int half = tid / kGreekContracts;  // warp-uniform split of the staging work
     const long long i = (long long)blockIdx.x * kGreekContracts + c;
-    const unsigned want = (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
-                          (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
+    const unsigned want = FULL ? 63u
+                               : (price ? W_PRICE : 0u) | (delta ? W_DELTA : 0u) | (gamma ? W_GAMMA : 0u) | (theta ? W_THETA : 0u) |
+                                     (rho ? W_RHO : 0u) | (vega ? W_VEGA : 0u);
     const bool valid = i < n;
     double Si = 0, Ki = 0, ti = 0, f = 1, ri = 0, sg = 0, qi = 0;
     if (valid) {
-        f = (double)flag[i * st.s[0]];
-        Si = S[i * st.s[1]];
-        Ki = K[i * st.s[2]];
-        ti = t[i * st.s[3]];
-        ri = r[i * st.s[4]];
-        sg = sigma[i * st.s[6]];
-        if (BSM) qi = q[i * st.s[5]];
+        if (FULL) {
+            f = (double)flag[i];
+            Si = S[i];
+            Ki = K[i];
+            ti = t[i];
+            ri = r[i];
+            sg = sigma[i];
+            if (BSM) qi = q[i];
+        } else {
+            f = (double)flag[i * st.s[0]];
+            Si = S[i * st.s[1]];
+            Ki = K[i * st.s[2]];
+            ti = t[i * st.s[3]];
+            ri = r[i * st.s[4]];
+            sg = sigma[i * st.s[6]];
+            if (BSM) qi = q[i * st.s[5]];
+        }
     }
     unsigned status = 0;
-    stage_greeks<BSM, kTileItems>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, stencil_need(want), status);
+    stage_greeks<BSM, kTileItems>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, FULL ? 0xffu : stencil_need(want), status);
     if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
     __syncthreads();  // the sort classifies items staged by other threads (two threads per contract)
     pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(
@@ -748,8 +761,23 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 2) { allow_smem(greeks_kernel<2>, sizeof(PriceTileShared)); greeks_kernel<2><<<grid_tiles(n, kGreekContracts), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base); }
-    else { allow_smem(greeks_kernel<1>, sizeof(PriceTileShared)); greeks_kernel<1><<<grid_tiles(n, kGreekContracts), kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, theta, rho, vega, fz, base); }
+    bool full = price && delta && gamma && theta && rho && vega;
+    for (int k = 0; k < 7 && full; ++k) full = st.s[k] == 1 || (k == 5 && model != 2);
+    const int grid = grid_tiles(n, kGreekContracts);
+#define PVV_GREEKS(M, F)                                                                                                            \
+    do {                                                                                                                            \
+        allow_smem(greeks_kernel<M, F>, sizeof(PriceTileShared));                                                                   \
+        greeks_kernel<M, F><<<grid, kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, \
+                                                                                theta, rho, vega, fz, base);                         \
+    } while (0)
+    if (model == 2) {
+        if (full) PVV_GREEKS(2, true);
+        else PVV_GREEKS(2, false);
+    } else {
+        if (full) PVV_GREEKS(1, true);
+        else PVV_GREEKS(1, false);
+    }
+#undef PVV_GREEKS
     g_launches++;
     return launch_status();
 }
