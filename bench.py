@@ -71,7 +71,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ceiling", action="store_true", help="measure the copy-only ceiling of the e2e traffic (always on for N > 1)")
+    ap.add_argument("--ceiling", action="store_true", help="(kept for compatibility: the copy-only ceiling of the e2e traffic is always measured)")
     return ap.parse_args()
 
 
@@ -593,7 +593,7 @@ class Bench:
                                   "pvv_*_host C-ABI call on PRE-PINNED host buffers, wall clock: short calls (<= 1.5 Mi contracts; K4: 128 Ki) are one launch "
                                   "that reads and writes the host memory over PCIe (zero-copy), longer ones the chunked 3-stream H2D/kernel/D2H pipeline; "
                                   "from pageable numpy / pandas the public API adds one staging copy (DESIGN.md section 6: 0.36 G contracts/s at 10 M rows)")}
-            if (args.ceiling or self.world > 1) and wl != "surface":
+            if wl != "surface":
                 csec = self.copy_ceiling(n, bytes_in, bytes_out)
                 res["e2e"]["ceiling"] = {"value": done / csec, "unit": "contracts/s", "gbs_both_directions": self.world * n * (bytes_in + bytes_out) / csec / 1e9,
                                          "frac": (done / sec) / (done / csec),
