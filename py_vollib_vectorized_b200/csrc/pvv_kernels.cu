@@ -1270,7 +1270,9 @@ int pvv_analytic_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *f
                             return pvv_analytic_greeks_dev(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, price ? v.out[0] : nullptr,
                                                            delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr, theta ? v.out[3] : nullptr,
                                                            rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr, s);
-                        });
+                        },
+                        zero_copy_max_iv_greeks());  // K5 streams its inputs with TMA bulk copies from two CTAs per SM: over a zero-copy
+                                                     // mapping that is too few reads in flight (0.66 vs 0.71 G contracts/s at 1 M)
 }
 
 // Host-side helper of the flag ingest (util/data_format.py): out[i] = vals[j] where in[i] == keys[j],

@@ -12,7 +12,7 @@ from py_vollib_vectorized_b200 import _engine as E  # noqa: E402
 from py_vollib_vectorized_b200.util.chains import chain_cfg2  # noqa: E402
 
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-for n in (1_000_000, 10_000_000):
+for n in [int(x) for x in os.environ.get("TUNE_N", "1000000,10000000").split(",")]:
     c = chain_cfg2(n, 0)
     h = {k: pin(c[k]) for k in ("flag", "S", "K", "t", "r", "sigma", "q")}
     out = {k: pin(np.empty(n)) for k in ("price", "delta", "gamma", "theta", "rho", "vega")}
