@@ -42,6 +42,10 @@ for seed, (lo, hi) in enumerate([(-300, 300), (-30, 30), (-5, 5), (-320, -280), 
     q = rng.uniform(-1, 1, n)
     for a in (S, K, t, sig, r, q):
         a[rng.random(n) < 0.002] = np.nan
+    if os.environ.get("FUZZ_INF"):  # infinities: outside the documented guarantee, reported separately
+        for a in (S, K, t, sig, r, q, ):
+            a[rng.random(n) < 0.002] = np.inf
+            a[rng.random(n) < 0.001] = -np.inf
     flag = np.where(rng.random(n) < .5, 1, -1).astype(np.int8)
     price = np.where(rng.random(n) < 0.5, ext(rng, n, lo, hi), np.minimum(S, K) * 10.0 ** rng.uniform(-320, 0.2, n))
     for model in ("black", "black_scholes", "black_scholes_merton"):
