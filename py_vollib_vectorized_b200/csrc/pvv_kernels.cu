@@ -39,6 +39,13 @@ __device__ __forceinline__ void note_zde(long long *first_zde, long long i) {
     if (first_zde) atomicMin(first_zde, i);
 }
 
+// Sets ST_ZERO_DIVISION in a status byte another kernel wrote (the greeks pass of the IV -> greeks route): an atomic OR on
+// the aligned word that holds the byte, because several threads may report the same contract and its neighbours.
+__device__ __noinline__ void or_status_zde(uint8_t *status, long long i) {
+    const unsigned long long a = (unsigned long long)(status + i);
+    atomicOr((unsigned *)(a & ~3ull), (unsigned)pvv::ST_ZERO_DIVISION << (8 * (unsigned)(a & 3ull)));
+}
+
 // ---- K1: price --------------------------------------------------------------------------------
 // Tile = 1024 contracts per CTA of 256 threads (4 per thread, strided so that global accesses stay
 // coalesced).  P1 stages each contract's (x, s, sqrt(F)sqrt(K), intrinsic, deflater) in shared
@@ -253,7 +260,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
                                                                  const double *__restrict__ sigma, Strides st, double *__restrict__ price,
                                                                  double *__restrict__ delta, double *__restrict__ gamma,
                                                                  double *__restrict__ theta, double *__restrict__ rho,
-                                                                 double *__restrict__ vega, long long *first_zde, long long base) {
+                                                                 double *__restrict__ vega, long long *first_zde, long long base,
+                                                                 uint8_t *status_or) {
     constexpr bool BSM = (MODEL == pvv::MODEL_BLACK_SCHOLES_MERTON);
     PriceTileShared &psh = *reinterpret_cast<PriceTileShared *>(dyn_smem);
     pvv::PriceItems<kTileItems> &items = psh.items;
@@ -289,10 +297,16 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
     }
     unsigned status = 0;
     stage_greeks<BSM, kTileItems>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, FULL ? 0xffu : stencil_need(want), status);
-    if (status & pvv::ST_ZERO_DIVISION) note_zde(first_zde, base + i);
+    if (status & pvv::ST_ZERO_DIVISION) {
+        note_zde(first_zde, base + i);
+        if (status_or) or_status_zde(status_or, i);
+    }
     __syncthreads();  // the sort classifies items staged by other threads (two threads per contract)
-    pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(
-        items, ts, [&](int item) { note_zde(first_zde, base + (long long)blockIdx.x * kGreekContracts + (item % kGreekContracts)); });
+    pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(items, ts, [&](int item) {
+        const long long iz = (long long)blockIdx.x * kGreekContracts + (item % kGreekContracts);
+        note_zde(first_zde, base + iz);
+        if (status_or) or_status_zde(status_or, iz);
+    });
     if (!valid || half != 0) return;
     finish_greeks(items, c, i, f, Si, Ki, ti, price, delta, gamma, theta, rho, vega);
 }
@@ -754,7 +768,8 @@ static int launch_price(int model, int64_t n, const int8_t *flag, const double *
 
 static int launch_greeks(int model, int64_t n, const int8_t *flag, const double *S, const double *K, const double *t, const double *r,
                          const double *q, const double *sigma, const int64_t stride[7], double *price, double *delta, double *gamma,
-                         double *theta, double *rho, double *vega, int64_t *first_zde, long long base, void *stream) {
+                         double *theta, double *rho, double *vega, int64_t *first_zde, long long base, void *stream,
+                         uint8_t *status_or = nullptr) {
     Strides st;
     if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
     if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
@@ -768,7 +783,7 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     do {                                                                                                                            \
         allow_smem(greeks_kernel<M, F>, sizeof(PriceTileShared));                                                                   \
         greeks_kernel<M, F><<<grid, kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, \
-                                                                                theta, rho, vega, fz, base);                         \
+                                                                                theta, rho, vega, fz, base, status_or);              \
     } while (0)
     if (model == 2) {
         if (full) PVV_GREEKS(2, true);
@@ -798,14 +813,33 @@ static int launch_iv(int model, int64_t n, const int8_t *flag, const double *pri
     return launch_status();
 }
 
+// PVV_IVG_FUSED=1 routes device-resident and chunked IV -> greeks calls through the single fused kernel again (A/B runs;
+// read at every call, so a process can time both).
+static bool ivg_fused_env() {
+    const char *e = getenv("PVV_IVG_FUSED");
+    return e && e[0] == '1';
+}
+
 static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K,
                             const double *t, const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv,
                             uint8_t *status, double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde,
-                            long long base, void *stream) {
+                            long long base, void *stream, bool fused) {
     Strides st;
-    if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
+    if (n < 0 || model < 0 || model > 2 || !iv || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
     if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
     if (n == 0) return 0;
+    if (!fused) {
+        // Two launches on one stream: K3 writes sigma (the iv column, masked as the caller asked) and the status bytes, K2
+        // evaluates the greeks at it and ORs its own zero divisions into them.  Every size measured prefers this to the
+        // fused kernel (12.5 M contracts: 2.88 vs 2.67 G/s; 128 Ki: 1.51 vs 1.06; tools/probe_k4_split.py): each pass
+        // keeps its own tile shape (3072 contracts per CTA for the solve, four 128-contract CTAs per SM for the stencil),
+        // and the 16 B per contract that sigma spends in HBM are invisible next to 3000 DP instructions.
+        int rc = launch_iv(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, first_zde, base, stream);
+        if (rc != 0 || !(delta || gamma || theta || rho || vega)) return rc;
+        const int64_t gst[7] = {stride[0], stride[2], stride[3], stride[4], stride[5], stride[6], 1};
+        return launch_greeks(model == 2 ? 2 : 1, n, flag, S, K, t, r, q, iv, gst, nullptr, delta, gamma, theta, rho, vega, first_zde,
+                             base, stream, status);
+    }
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
     if (model == 0)
@@ -836,7 +870,7 @@ int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const double *pr
                       const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
                       double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream) {
     return launch_iv_greeks(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, delta, gamma, theta, rho, vega,
-                            first_zde, 0, stream);
+                            first_zde, 0, stream, ivg_fused_env());
 }
 
 int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void *stream) {
@@ -934,6 +968,7 @@ struct SlotView {
     double *out[kOutCols];
     int8_t *flag;
     uint8_t *status;
+    bool zero_copy = false;  // the pointers are mappings of the caller's pinned host buffers, not a device slot
 };
 inline SlotView view(const pvv_ctx *c, int i) {
     SlotView v;
@@ -1083,6 +1118,7 @@ int run_pipeline(pvv_ctx *c, long long n, const int8_t *flag, long long flag_str
     if (n <= (zc_max >= 0 ? zc_max : zero_copy_max())) {
         bool ok = true;
         SlotView z{};
+        z.zero_copy = true;
         const double *zin[kInCols] = {nullptr};
         for (int j = 0; j < n_in && ok; ++j) {
             if (!in[j]) continue;
@@ -1251,7 +1287,7 @@ int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, c
                             return launch_iv_greeks(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, mask_errors, v.out[0],
                                                     v.status, delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr,
                                                     theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
-                                                    (int64_t *)ctx->first_zde, off, s);
+                                                    (int64_t *)ctx->first_zde, off, s, v.zero_copy || ivg_fused_env());
                         },
                         zero_copy_max_iv_greeks());
 }

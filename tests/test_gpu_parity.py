@@ -266,3 +266,59 @@ def test_device_pointer_entry_points(eng, oracle, golden):
     assert_bit_equal(ref_o["iv"], iv_h, "fused IV")
     for k in GREEKS:
         assert_bit_equal(ref_o[k], outs[k].cpu().numpy(), f"fused {k}")
+
+
+def test_iv_greeks_routes_agree(eng, oracle, monkeypatch):
+    """pvv_iv_greeks_dev's default route (K3, then K2 at the solved volatility, which ORs its own zero divisions into the
+    status bytes K3 wrote) against the single fused kernel (PVV_IVG_FUSED=1) and the oracle: values, status and the
+    first-ZeroDivisionError index, on a chain with rows whose ONLY zero division sits in the greeks pass
+    (exp(-(r + 0.01) t) underflows to zero although exp(-r t) does not), for every subset size the stencil prunes by."""
+    import torch
+    rng = np.random.default_rng(77)
+    n = 70_001  # ragged against every tile size, odd so the status word of the last byte is shared
+    S = rng.uniform(50, 150, n)
+    K = S * rng.uniform(0.6, 1.5, n)
+    t = rng.uniform(0.02, 2.0, n)
+    r = rng.uniform(0.0, 0.08, n)
+    sig = rng.uniform(0.05, 0.9, n)
+    flag = np.where(rng.random(n) < 0.5, 1, -1).astype(np.int8)
+    price, _ = oracle.price("black_scholes", flag, S, K, t, r, sig)
+    price[rng.random(n) < 0.01] *= 0.2   # below intrinsic: NaN sigma goes into the greeks pass
+    price[rng.random(n) < 0.01] *= 50.0  # above maximum
+    late = np.array([5, 4097, 4098, 4099, 33_333, n - 1])  # neighbours share a status word
+    t[late], r[late] = 100.0, 7.445       # exp(-744.5) is a subnormal, exp(-745.5) is zero
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(flag=flag, price=price, S=S, K=K, t=t, r=r).items()}
+    ref, st_ref, zde_ref = oracle.iv_greeks("black_scholes", price, S, K, t, r, flag)
+    assert (st_ref[late] & 4).all() and zde_ref == 5
+    st_iv = oracle.iv("black_scholes", price, S, K, t, r, flag)[1]
+    assert not (st_iv[late] & 4).any()  # the solve alone does not divide by zero on those rows
+
+    def run(want):
+        iv = torch.empty(n, dtype=torch.float64, device="cuda")
+        st = torch.empty(n, dtype=torch.uint8, device="cuda")
+        outs = {k: torch.empty(n, dtype=torch.float64, device="cuda") for k in want}
+        zde = eng.new_zde_word("cuda")
+        eng.iv_greeks_dev("black_scholes", n, d["flag"], d["price"], d["S"], d["K"], d["t"], d["r"], None, iv, st, outs, first_zde=zde)
+        torch.cuda.synchronize()
+        return iv.cpu().numpy(), st.cpu().numpy(), {k: v.cpu().numpy() for k, v in outs.items()}, zde.item()
+
+    for want in (GREEKS, ("rho",), ("delta", "vega")):
+        monkeypatch.setenv("PVV_IVG_FUSED", "0")
+        before = eng.launch_count()
+        iv_a, st_a, o_a, z_a = run(want)
+        assert eng.launch_count() - before == 2  # K3 + K2
+        monkeypatch.setenv("PVV_IVG_FUSED", "1")
+        before = eng.launch_count()
+        iv_b, st_b, o_b, z_b = run(want)
+        assert eng.launch_count() - before == 1
+        assert_bit_equal(iv_a, iv_b, "iv")
+        assert (st_a == st_b).all() and z_a == z_b
+        for k in want:
+            assert_bit_equal(o_a[k], o_b[k], k)
+        if "rho" in want:  # the r +- 0.01 stencil points are the ones that divide by zero
+            assert z_a == zde_ref and (st_a == st_ref).all()
+            ok = (st_ref & 4) == 0
+            assert_bit_equal(ref["iv"][ok], iv_a[ok], "iv vs oracle")
+            for k in want:
+                assert_bit_equal(ref[k][ok], o_a[k][ok], f"{k} vs oracle")
+    monkeypatch.setenv("PVV_IVG_FUSED", "0")

@@ -1,7 +1,7 @@
 """DP instructions and DRAM bytes per contract from ncu --set full captures -> profiles/dp_per_contract.json
 (read by bench.py for the FP64 roofline, so that the figures follow the kernels instead of living in the source):
 
-    python tools/ncu_dp_counts.py TAG workload=rep.ncu-rep:contracts [workload=rep:contracts ...]
+    python tools/ncu_dp_counts.py TAG workload=rep.ncu-rep:contracts [workload=repA+repB:contracts ...]
 
 dp_inst  = DFMA+DMUL+DADD+DSETP+DMNMX executed on ACTIVE lanes / contracts (the algorithmic work),
 dp_slots = warp-level DP issues x 32 / contracts (what occupies the FP64 pipe, inactive lanes included),
@@ -58,7 +58,17 @@ if __name__ == "__main__":
     for a in sys.argv[2:]:
         wl, rest = a.split("=")
         rep, n = rest.rsplit(":", 1)
-        table["kernels"][wl] = counts(rep, int(n))
+        parts = [counts(x, int(n)) for x in rep.split("+")]  # a workload of several launches per step: repA+repB
+        tot = dict(parts[0])
+        for q in parts[1:]:
+            for k in ("dp_inst", "dp_slots", "inst_slots", "traffic_bytes", "duration_us"):
+                tot[k] = round(tot[k] + q[k], 1)
+            tot["kernel"] += " + " + q["kernel"]
+            tot["report"] += " + " + q["report"]
+        if len(parts) > 1:
+            for k in ("fp64_pipe_pct", "issue_active_pct"):  # time-weighted over the launches of one step
+                tot[k] = round(sum(q[k] * q["duration_us"] for q in parts) / sum(q["duration_us"] for q in parts), 2)
+        table["kernels"][wl] = tot
         table["kernels"][wl]["capture"] = tag
         print(wl, table["kernels"][wl])
     table["source"] = f"ncu --set full captures, tools/ncu_dp_counts.py; per-kernel `capture` tags name the profiles/ summary"

@@ -12,6 +12,14 @@ for V in ${VARIANTS:-main}; do
     [ "$W" = "greeks" ] && K="^greeks_kernel"
     [ "$W" = "analytic" ] && N="--n 4000000" && K="analytic_kernel_tma"
     C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline $N"
+    if [ "$W" = "iv_greeks" ] && [ "${PVV_IVG_FUSED:-0}" != "1" ]; then
+      # the IV -> greeks route is two launches per step: one capture of each on the workload's own chain
+      for P in iv greeks; do
+        ncu --set full --clock-control none --import-source on -k regex:^${P}_kernel -s 3 -c 1 -o gpurun_out/${TAG}_${V}_${W}_$P -f $C > gpurun_out/${TAG}_${V}_${W}_${P}_ncu.log 2>&1
+        tail -2 gpurun_out/${TAG}_${V}_${W}_${P}_ncu.log
+      done
+      continue
+    fi
     ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/${TAG}_${V}_$W -f $C > gpurun_out/${TAG}_${V}_${W}_ncu.log 2>&1
     tail -2 gpurun_out/${TAG}_${V}_${W}_ncu.log
   done
