@@ -47,7 +47,7 @@ WORKLOADS = {
     "iv": ("IV solves/s", "black_scholes_merton", 10_000_000, 49, 9,
            "cfg3: 10M-contract BSM implied volatility with deep-OTM / short-expiry / below-intrinsic strata (kernel K3)"),
     "iv_greeks": ("IV+greeks contracts/s", "black_scholes", 12_500_000, 41, 49,
-                  "cfg4: mixed call/put chain, IV then greeks at the solved vol (kernel K4), 12.5M contracts per GPU"),
+                  "cfg4: mixed call/put chain, IV then greeks at the solved vol (K4 route: K3 then K2 on one stream), 12.5M contracts per GPU"),
     "analytic": ("price+analytical-greeks contracts/s", "black_scholes", 16_000_000, 41, 48,
                  "opt-in closed-form greeks (SURVEY 8(f).3): 16M-contract Black-Scholes chain, price + 5 analytical greeks, one HBM-bound pass"),
     "surface": ("price_dataframe rows/s", "black", 10_000_000, 41, 48,
@@ -621,7 +621,8 @@ class Bench:
                                "how": "the engine is compiled without FMA contraction (parity), so one DP instruction is one flop: achieved = contracts/s x DP "
                                       "instructions per contract executed on active lanes (ncu capture named in `source`); peak = dependent DMUL+DADD chains "
                                       "measured in this run; pipe_frac counts warp-level issues x 32 (inactive lanes occupy the pipe too; compare ncu's "
-                                      "sm__pipe_fp64_cycles_active); traffic = ncu dram read+write bytes per launch",
+                                      "sm__pipe_fp64_cycles_active); traffic = ncu dram read+write bytes per launch"
+                                      + (" (IV -> greeks: a step is two launches, K3 then K2; counts, traffic and the time are those of the pair)" if wl == "iv_greeks" else ""),
                                "hbm": {k: hbm[k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes", "peak_source")}}
         if self.world > 1 and wl in ("greeks", "price", "iv", "iv_greeks"):
             ok = self.parity_sample(wl, sets[0], n)

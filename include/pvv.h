@@ -84,6 +84,11 @@ PVV_API int pvv_iv_dev(int model, int64_t n, const int8_t *flag, const double *p
                const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
                int64_t *first_zde, void *stream);
 
+/* The price_col branch of price_dataframe (api.py:142-178) in one call: the solve, then the finite-difference greeks at
+ * the solved (and, with mask_errors, masked) volatility.  `iv` is required (it carries sigma from the first pass to
+ * the second); status bit 4 and first_zde cover zero divisions of BOTH passes.  Device-resident and chunked calls are
+ * two launches on `stream` (K3, then K2: measured faster than one fused kernel at every size);
+ * short zero-copy host calls keep the single fused kernel. */
 PVV_API int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
                       const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
                       double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream);

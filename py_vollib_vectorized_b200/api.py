@@ -4,8 +4,8 @@ Public surface of /root/reference/py_vollib_vectorized/api.py (:19-181, :184-256
 runs five numba passes for the greeks (11 price evaluations per contract, 8 distinct) and re-runs
 flag pre-processing and broadcasting three to four times per `price_dataframe` call; here one
 flag encode + one broadcast feed kernel K2 (all five greeks from the 8 distinct stencil points in
-one pass) or, when only prices are given, kernel K4 (implied volatility and the greeks at the
-solved volatility in one pass, sigma never leaves the device).
+one pass) or, when only prices are given, the K4 route (one call: implied volatility, then the
+greeks at the solved volatility; sigma never leaves the device).
 
 Deliberate differences (values are identical):
   * `get_all_greeks(return_as != "dataframe")` returns a dict of numpy arrays, where the reference
@@ -152,7 +152,7 @@ def price_dataframe(df, *, flag_col=None, underlying_price_col=None, strike_col=
 
     results = {}
     if _iv_calc:
-        # K4: implied volatility and the greeks at that volatility in one pass (api.py:142-178)
+        # K4: implied volatility and the greeks at that volatility in one call (api.py:142-178)
         outs, status, _ = _engine.iv_greeks(model, c.n, flag, price_c, S, K, t, r, q_c, mask_errors=True)
         report_iv_status(status, "warn")
         results["IV"] = outs["iv"]
