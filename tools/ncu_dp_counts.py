@@ -46,7 +46,9 @@ def counts(rep, contracts):
             "traffic_bytes": round(traffic / contracts, 1), "contracts": contracts, "kernel": vals[hh.index("Kernel Name")][:60],
             "fp64_pipe_pct": float(vals[hh.index("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")]),
             "issue_active_pct": float(vals[hh.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
-            "duration_us": float(vals[hh.index("gpu__time_duration.sum")].replace(",", "")), "report": os.path.basename(rep)}
+            "duration_us": round(float(vals[hh.index("gpu__time_duration.sum")].replace(",", ""))
+                                 * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hh.index("gpu__time_duration.sum")], 1.0), 3),
+            "report": os.path.basename(rep)}
 
 
 if __name__ == "__main__":

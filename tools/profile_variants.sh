@@ -11,10 +11,13 @@ for V in ${VARIANTS:-main}; do
     [ "$W" = "iv_greeks" ] && N="--n 2000000"
     [ "$W" = "greeks" ] && K="^greeks_kernel"
     [ "$W" = "analytic" ] && N="--n 4000000" && K="analytic_kernel_tma"
-    C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline $N"
-    if [ "$W" = "iv_greeks" ] && [ "${PVV_IVG_FUSED:-0}" != "1" ]; then
-      # the IV -> greeks route is two launches per step: one capture of each on the workload's own chain
-      for P in iv greeks; do
+    C="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline --no-e2e $N"
+    PARTS=""
+    [ "$W" = "iv_greeks" ] && [ "${PVV_IVG_FUSED:-0}" != "1" ] && PARTS="iv greeks"
+    [ "$W" = "surface" ] && PARTS="price greeks"
+    if [ -n "$PARTS" ]; then
+      # two launches per step (IV -> greeks: K3 then K2; cfg5 surface: K1 then K2): one capture of each on the workload's own chain
+      for P in $PARTS; do
         ncu --set full --clock-control none --import-source on -k regex:^${P}_kernel -s 3 -c 1 -o gpurun_out/${TAG}_${V}_${W}_$P -f $C > gpurun_out/${TAG}_${V}_${W}_${P}_ncu.log 2>&1
         tail -2 gpurun_out/${TAG}_${V}_${W}_${P}_ncu.log
       done
