@@ -50,9 +50,15 @@ __device__ __noinline__ void or_status_zde(uint8_t *status, long long i) {
 // Tile = 1024 contracts per CTA of 256 threads (4 per thread, strided so that global accesses stay
 // coalesced).  P1 stages each contract's (x, s, sqrt(F)sqrt(K), intrinsic, deflater) in shared
 // memory, P2 evaluates b(x, s) in region-sorted order (pvv_tile.cuh), P3 stores the prices.
-constexpr int kTileThreads = 256;
+#ifndef PVV_TILE_THREADS
+#define PVV_TILE_THREADS 256  // measured: 128 / 192 / 256 / 512 threads per CTA (tools/ab_perf.sh), DESIGN.md section 5
+#endif
+#ifndef PVV_TILE_IPT
+#define PVV_TILE_IPT 4
+#endif
+constexpr int kTileThreads = PVV_TILE_THREADS;
 constexpr int kTileCtasPerSm = 1024 / kTileThreads;
-constexpr int kItemsPerThread = 4;
+constexpr int kItemsPerThread = PVV_TILE_IPT;
 constexpr int kTileItems = kTileThreads * kItemsPerThread;
 constexpr int kGreekContracts = kTileItems / 8;  // contracts per CTA of the greeks kernel: 8 stencil points each
 
