@@ -495,15 +495,16 @@ __device__ __forceinline__ double iv_tile_vol(const IvTile<NT, IPT> &sh, int c, 
     return (mask_errors && (status & (pvv::ST_BELOW_INTRINSIC | pvv::ST_ABOVE_MAXIMUM))) ? pvv::u2d(0x7ff8000000000000ull) : vol;
 }
 
-// K3 comes in two shapes: 1024 threads x 3 contracts (one CTA per SM, 3072 contracts, 189 KB of shared memory)
-// for long columns, 512 threads x 3 contracts (two CTAs per SM, 1536 contracts each) for short ones, where the
-// last wave of big tiles would leave most SMs idle and a tile's latency shows (the host pipeline's 512 Ki-contract
-// chunks: 0.99 G IV/s end to end with the small shape, 0.95 with 2048-contract tiles).
+// K3 comes in two shapes: 1024 threads x 3 contracts (one CTA per SM, up to 3072 contracts, 189 KB of shared
+// memory), and 512 threads x 3 contracts (two CTAs per SM, up to 1536 contracts each) for calls of a few thousand
+// contracts.  Tiles are filled evenly (iv_tile_plan), so a partial last wave no longer decides between them; measured
+// with tools/probe_iv_sizes.py the big shape wins from 64 Ki contracts on (128 Ki: 43 vs 48 us, 512 Ki: 107 vs 117 us,
+// 1 M: 184 vs 194 us).
 #ifndef PVV_IV_NT
 #define PVV_IV_NT 1024
 #define PVV_IV_IPT 3
 #endif
-constexpr long long kIvBigTileMin = 4ll * 148 * PVV_IV_NT * PVV_IV_IPT;  // at least four full waves of big tiles
+constexpr long long kIvBigTileMin = 65536;  // with even tiles the big shape wins from 64 Ki contracts on (tools/probe_iv_sizes.py)
 
 template <int MODEL, int NT, int IPT>
 __global__ void __launch_bounds__(NT, (NT > 512 ? 1 : 1024 / NT)) iv_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ price,
@@ -511,10 +512,13 @@ __global__ void __launch_bounds__(NT, (NT > 512 ? 1 : 1024 / NT)) iv_kernel(long
                                                            const double *__restrict__ t, const double *__restrict__ r,
                                                            const double *__restrict__ q, Strides st, int mask_errors,
                                                            double *__restrict__ iv, uint8_t *__restrict__ status_out, long long *first_zde,
-                                                           long long base) {
+                                                           long long base, int cpt) {
     using Tile = IvTile<NT, IPT>;
     Tile &sh = *reinterpret_cast<Tile *>(dyn_smem);
-    const long long tile0 = (long long)blockIdx.x * Tile::C;
+    // the CTA owns contracts [tile0, tile0 + cpt), cpt <= Tile::C chosen by the launch so that the tiles fill whole
+    // waves evenly (iv_tile_plan); slots beyond cpt are treated like the ragged tail of the column
+    const long long tile0 = (long long)blockIdx.x * cpt;
+    if (tile0 + cpt < n) n = tile0 + cpt;
     iv_tile_front<MODEL>(sh, tile0, n, flag, price, S, K, t, r, q, st);
     iv_tile_solve2(sh);
 #pragma unroll 1
@@ -707,18 +711,56 @@ inline void allow_smem(Kern k, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// SMs of the current device (cached per device: a process may drive several)
+inline int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = v > 0 ? v : 148;
+    }
+    return cache[dev];
+}
+
+// Contracts per tile for a K3 launch.  A tile is a long sequential program (50-70 us), so a last wave that fills a
+// fraction of the SMs costs a whole tile time, and a short column occupies only n / capacity SMs.  Instead of full
+// tiles plus a remainder, the column is cut into waves x slots equal tiles (slots = SMs x resident CTAs), each
+// a multiple of 32 contracts so that every tile starts on a 256-byte boundary of the columns.  PVV_IV_EVEN_TILES=0
+// restores full tiles (A/B runs).
+inline int iv_tile_plan(long long n, int capacity, int ctas_per_sm) {
+    static const bool even = [] { const char *e = getenv("PVV_IV_EVEN_TILES"); return !(e && e[0] == '0'); }();
+    if (!even) return capacity;
+    const long long slots = (long long)sm_count() * ctas_per_sm;
+    const long long waves = (n + slots * capacity - 1) / (slots * capacity);
+    long long cpt = (n + waves * slots - 1) / (waves * slots);
+    cpt = (cpt + 31) / 32 * 32;
+    return (int)(cpt > capacity ? capacity : cpt);
+}
+// host_path: launches of the host entry points (chunks of the copy pipeline, zero-copy calls).  There the kernel shares
+// the GPU with the DMA traffic of its neighbours, and the two-CTA shape is the better citizen up to four full waves of
+// big tiles: 10 M BSM contracts end to end 0.960 vs 0.938 G IV/s, A/B on the same box.
+inline long long iv_big_tile_min(bool host_path) {
+    static const long long v = [] { const char *e = getenv("PVV_IV_BIG_MIN"); return e ? atoll(e) : -1ll; }();
+    if (v >= 0) return v;
+    return host_path ? 4ll * 148 * PVV_IV_NT * PVV_IV_IPT : kIvBigTileMin;
+}
+
 template <int MODEL>
 inline void launch_iv_shape(long long n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
                             const double *r, const double *q, const Strides &st, int mask_errors, double *iv, uint8_t *status, long long *fz,
-                            long long base, cudaStream_t s) {
-    if (n >= kIvBigTileMin) {
+                            long long base, cudaStream_t s, bool host_path) {
+    if (n >= iv_big_tile_min(host_path)) {
         using Tile = IvTile<PVV_IV_NT, PVV_IV_IPT>;
+        const int cpt = iv_tile_plan(n, Tile::C, 1);
         allow_smem(iv_kernel<MODEL, PVV_IV_NT, PVV_IV_IPT>, sizeof(Tile));
-        iv_kernel<MODEL, PVV_IV_NT, PVV_IV_IPT><<<grid_tiles(n, Tile::C), PVV_IV_NT, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        iv_kernel<MODEL, PVV_IV_NT, PVV_IV_IPT><<<grid_tiles(n, cpt), PVV_IV_NT, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, cpt);
     } else {
         using Tile = IvTile<512, 3>;
+        const int cpt = iv_tile_plan(n, Tile::C, 2);
         allow_smem(iv_kernel<MODEL, 512, 3>, sizeof(Tile));
-        iv_kernel<MODEL, 512, 3><<<grid_tiles(n, Tile::C), 512, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base);
+        iv_kernel<MODEL, 512, 3><<<grid_tiles(n, cpt), 512, sizeof(Tile), s>>>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, cpt);
     }
 }
 
@@ -805,16 +847,16 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
 
 static int launch_iv(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K, const double *t,
                      const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv, uint8_t *status,
-                     int64_t *first_zde, long long base, void *stream) {
+                     int64_t *first_zde, long long base, void *stream, bool host_path = false) {
     Strides st;
     if (n < 0 || model < 0 || model > 2 || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
     if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     long long *fz = (long long *)first_zde;
-    if (model == 0) launch_iv_shape<0>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
-    else if (model == 1) launch_iv_shape<1>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
-    else launch_iv_shape<2>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s);
+    if (model == 0) launch_iv_shape<0>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s, host_path);
+    else if (model == 1) launch_iv_shape<1>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s, host_path);
+    else launch_iv_shape<2>(n, flag, price, S, K, t, r, q, st, mask_errors, iv, status, fz, base, s, host_path);
     g_launches++;
     return launch_status();
 }
@@ -829,7 +871,7 @@ static bool ivg_fused_env() {
 static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const double *price, const double *S, const double *K,
                             const double *t, const double *r, const double *q, const int64_t stride[7], int mask_errors, double *iv,
                             uint8_t *status, double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde,
-                            long long base, void *stream, bool fused) {
+                            long long base, void *stream, bool fused, bool host_path = false) {
     Strides st;
     if (n < 0 || model < 0 || model > 2 || !iv || !fill_strides(stride, st)) return PVV_E_INVALID_ARGUMENT;
     if (model == 2 && !q) return PVV_E_INVALID_ARGUMENT;
@@ -840,7 +882,7 @@ static int launch_iv_greeks(int model, int64_t n, const int8_t *flag, const doub
         // fused kernel (12.5 M contracts: 2.88 vs 2.67 G/s; 128 Ki: 1.51 vs 1.06; tools/probe_k4_split.py): each pass
         // keeps its own tile shape (3072 contracts per CTA for the solve, four 128-contract CTAs per SM for the stencil),
         // and the 16 B per contract that sigma spends in HBM are invisible next to 3000 DP instructions.
-        int rc = launch_iv(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, first_zde, base, stream);
+        int rc = launch_iv(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, first_zde, base, stream, host_path);
         if (rc != 0 || !(delta || gamma || theta || rho || vega)) return rc;
         const int64_t gst[7] = {stride[0], stride[2], stride[3], stride[4], stride[5], stride[6], 1};
         return launch_greeks(model == 2 ? 2 : 1, n, flag, S, K, t, r, q, iv, gst, nullptr, delta, gamma, theta, rho, vega, first_zde,
@@ -1275,7 +1317,7 @@ int pvv_iv_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, const do
     return run_pipeline(ctx, n, flag, stride[0], 7, in, ist, 1, out, status, first_zde,
                         [&](const SlotView &v, const double *const *d, const int8_t *df, long long m, long long off, cudaStream_t s) {
                             return launch_iv(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, mask_errors, v.out[0], v.status,
-                                             (int64_t *)ctx->first_zde, off, s);
+                                             (int64_t *)ctx->first_zde, off, s, true);
                         });
 }
 
@@ -1293,7 +1335,7 @@ int pvv_iv_greeks_host(pvv_ctx *ctx, int model, int64_t n, const int8_t *flag, c
                             return launch_iv_greeks(model, m, df, d[1], d[2], d[3], d[4], d[5], d[6], stride, mask_errors, v.out[0],
                                                     v.status, delta ? v.out[1] : nullptr, gamma ? v.out[2] : nullptr,
                                                     theta ? v.out[3] : nullptr, rho ? v.out[4] : nullptr, vega ? v.out[5] : nullptr,
-                                                    (int64_t *)ctx->first_zde, off, s, v.zero_copy || ivg_fused_env());
+                                                    (int64_t *)ctx->first_zde, off, s, v.zero_copy || ivg_fused_env(), true);
                         },
                         zero_copy_max_iv_greeks());
 }
