@@ -42,8 +42,8 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_extension(force=False, verbose=False, variant=None, defines=()):
-    """variant/defines: A/B builds for kernel experiments -> build/libpvv_<variant>.so (loaded with PVV_LIB=...)."""
+def build_extension(force=False, verbose=False, variant=None, defines=(), extra_flags=()):
+    """variant/defines/extra_flags: A/B builds for kernel experiments -> build/libpvv_<variant>.so (loaded with PVV_LIB=...)."""
     if variant is None and not force and not needs_build():
         return LIB
     # the image's default CC wrapper lacks some specs; the system g++ is the host compiler
@@ -52,7 +52,7 @@ def build_extension(force=False, verbose=False, variant=None, defines=()):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     lib = LIB if variant is None else os.path.join(HERE, "build", f"libpvv_{variant}.so")
-    defs = [f"-D{d}" for d in defines]
+    defs = [f"-D{d}" for d in defines] + list(extra_flags)
 
     def run(cmd):
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -70,7 +70,8 @@ def build_extension(force=False, verbose=False, variant=None, defines=()):
 
 
 if __name__ == "__main__":
-    # python build.py [--force] [--verbose] [--variant NAME -DFOO -DBAR=1 ...]
+    # python build.py [--force] [--verbose] [--variant NAME -DFOO -DBAR=1 ... --nvcc-flags "-Xptxas -dlcm=ca"]
     var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    xf = sys.argv[sys.argv.index("--nvcc-flags") + 1].split() if "--nvcc-flags" in sys.argv else []
     print(build_extension(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var,
-                          defines=[a[2:] for a in sys.argv if a.startswith("-D")]))
+                          defines=[a[2:] for a in sys.argv if a.startswith("-D")], extra_flags=xf))
