@@ -259,7 +259,9 @@ __device__ __forceinline__ void finish_greeks(const pvv::PriceItems<T> &items, i
 
 // FULL: every column dense and all six outputs wanted (get_all_greeks / price_dataframe): the stride multiplications, the
 // want / need bit tests of the staging loop and the null checks of the stores are compiled out.
-template <int MODEL, bool FULL>
+// ORSTAT: the greeks pass of the IV -> greeks route: zero divisions are ORed into the status bytes K3 wrote (`status_or`).
+// A separate instantiation, because even this cold path costs the plain kernel 1.5 % (4.98 -> 4.90 G/s, A/B on one box).
+template <int MODEL, bool FULL, bool ORSTAT = false>
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(long long n, const int8_t *__restrict__ flag, const double *__restrict__ S,
                                                                  const double *__restrict__ K, const double *__restrict__ t,
                                                                  const double *__restrict__ r, const double *__restrict__ q,
@@ -305,13 +307,13 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) greeks_kernel(lo
     stage_greeks<BSM, kTileItems>(items, c, half, valid, f, Si, Ki, ti, ri, sg, qi, FULL ? 0xffu : stencil_need(want), status);
     if (status & pvv::ST_ZERO_DIVISION) {
         note_zde(first_zde, base + i);
-        if (status_or) or_status_zde(status_or, i);
+        if (ORSTAT) or_status_zde(status_or, i);
     }
     __syncthreads();  // the sort classifies items staged by other threads (two threads per contract)
     pvv::eval_price_items<kTileThreads, kItemsPerThread, true>(items, ts, [&](int item) {
         const long long iz = (long long)blockIdx.x * kGreekContracts + (item % kGreekContracts);
         note_zde(first_zde, base + iz);
-        if (status_or) or_status_zde(status_or, iz);
+        if (ORSTAT) or_status_zde(status_or, iz);
     });
     if (!valid || half != 0) return;
     finish_greeks(items, c, i, f, Si, Ki, ti, price, delta, gamma, theta, rho, vega);
@@ -827,18 +829,21 @@ static int launch_greeks(int model, int64_t n, const int8_t *flag, const double 
     bool full = price && delta && gamma && theta && rho && vega;
     for (int k = 0; k < 7 && full; ++k) full = st.s[k] == 1 || (k == 5 && model != 2);
     const int grid = grid_tiles(n, kGreekContracts);
-#define PVV_GREEKS(M, F)                                                                                                            \
+#define PVV_GREEKS(M, F, O)                                                                                                         \
     do {                                                                                                                            \
-        allow_smem(greeks_kernel<M, F>, sizeof(PriceTileShared));                                                                   \
-        greeks_kernel<M, F><<<grid, kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, gamma, \
-                                                                                theta, rho, vega, fz, base, status_or);              \
+        allow_smem(greeks_kernel<M, F, O>, sizeof(PriceTileShared));                                                                \
+        greeks_kernel<M, F, O><<<grid, kTileThreads, sizeof(PriceTileShared), s>>>(n, flag, S, K, t, r, q, sigma, st, price, delta, \
+                                                                                   gamma, theta, rho, vega, fz, base, status_or);   \
     } while (0)
-    if (model == 2) {
-        if (full) PVV_GREEKS(2, true);
-        else PVV_GREEKS(2, false);
+    if (status_or) {
+        if (model == 2) PVV_GREEKS(2, false, true);
+        else PVV_GREEKS(1, false, true);
+    } else if (model == 2) {
+        if (full) PVV_GREEKS(2, true, false);
+        else PVV_GREEKS(2, false, false);
     } else {
-        if (full) PVV_GREEKS(1, true);
-        else PVV_GREEKS(1, false);
+        if (full) PVV_GREEKS(1, true, false);
+        else PVV_GREEKS(1, false, false);
     }
 #undef PVV_GREEKS
     g_launches++;
