@@ -158,6 +158,11 @@ PVV_API int pvv_fp64_probe(int64_t threads, int iters, int use_fma, float *ms, v
  * elapsed ms for iters x 16 DP instructions per thread over warps_per_sm x 32 threads on every SM */
 PVV_API int pvv_fp64_ilp_probe(int chains, int warps_per_sm, int iters, float *ms, void *stream);
 
+/* host logic, no device: contracts per K3 tile when a column of n contracts is cut into waves x slots equal tiles of at
+ * most `capacity` (multiple of 32) contracts; slots = SMs x resident CTAs.  Returns the tile size (multiple of 32,
+ * <= capacity) or PVV_E_INVALID_ARGUMENT. */
+PVV_API int pvv_iv_tile_plan(int64_t n, int capacity, int slots);
+
 #ifdef __cplusplus
 }
 #endif

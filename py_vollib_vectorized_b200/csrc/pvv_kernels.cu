@@ -731,14 +731,16 @@ inline int sm_count() {
 // tiles plus a remainder, the column is cut into waves x slots equal tiles (slots = SMs x resident CTAs), each
 // a multiple of 32 contracts so that every tile starts on a 256-byte boundary of the columns.  PVV_IV_EVEN_TILES=0
 // restores full tiles (A/B runs).
-inline int iv_tile_plan(long long n, int capacity, int ctas_per_sm) {
-    static const bool even = [] { const char *e = getenv("PVV_IV_EVEN_TILES"); return !(e && e[0] == '0'); }();
-    if (!even) return capacity;
-    const long long slots = (long long)sm_count() * ctas_per_sm;
+inline int iv_tile_plan_for(long long n, int capacity, long long slots) {
     const long long waves = (n + slots * capacity - 1) / (slots * capacity);
     long long cpt = (n + waves * slots - 1) / (waves * slots);
     cpt = (cpt + 31) / 32 * 32;
     return (int)(cpt > capacity ? capacity : cpt);
+}
+inline int iv_tile_plan(long long n, int capacity, int ctas_per_sm) {
+    static const bool even = [] { const char *e = getenv("PVV_IV_EVEN_TILES"); return !(e && e[0] == '0'); }();
+    if (!even) return capacity;
+    return iv_tile_plan_for(n, capacity, (long long)sm_count() * ctas_per_sm);
 }
 // host_path: launches of the host entry points (chunks of the copy pipeline, zero-copy calls).  There the kernel shares
 // the GPU with the DMA traffic of its neighbours, and the two-CTA shape is the better citizen up to four full waves of
@@ -924,6 +926,13 @@ int pvv_iv_greeks_dev(int model, int64_t n, const int8_t *flag, const double *pr
                       double *delta, double *gamma, double *theta, double *rho, double *vega, int64_t *first_zde, void *stream) {
     return launch_iv_greeks(model, n, flag, price, S, K, t, r, q, stride, mask_errors, iv, status, delta, gamma, theta, rho, vega,
                             first_zde, 0, stream, ivg_fused_env());
+}
+
+// host logic only (no device involved): contracts per K3 tile for a column of n contracts, tiles of at most `capacity`
+// contracts and `slots` = SMs x resident CTAs (tests/test_host_logic.py checks the plan's invariants)
+int pvv_iv_tile_plan(int64_t n, int capacity, int slots) {
+    if (n <= 0 || capacity < 32 || capacity % 32 || slots <= 0) return PVV_E_INVALID_ARGUMENT;
+    return iv_tile_plan_for(n, capacity, slots);
 }
 
 int pvv_unary_dev(int which, int64_t n, const double *x, double *y, void *stream) {

@@ -190,3 +190,31 @@ def test_scalar_q_with_vector_inputs_like_the_reference():
         assert pvv.vectorized_delta(*args, model="black", return_as="numpy", fix_reference_bugs=True).shape == (2,)
     except _engine.PvvError:
         pass
+
+
+def test_iv_tile_plan_invariants():
+    """K3's launch plan (pvv_iv_tile_plan, pure host logic): a column is cut into waves x slots equal tiles.  Whatever n:
+    the tiles cover the column, fit the tile capacity, start on 32-contract boundaries, use the minimal number of waves,
+    and no tile is more than one 32-contract step larger than an even split."""
+    import ctypes
+    from py_vollib_vectorized_b200 import _engine
+    lib = _engine.lib()
+    lib.pvv_iv_tile_plan.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    lib.pvv_iv_tile_plan.restype = ctypes.c_int
+    rng = np.random.default_rng(5)
+    sizes = [1, 31, 32, 33, 1000, 65535, 65536, 131072, 454655, 454656, 454657, 1_000_000, 10_000_000, 100_000_000, 2**40]
+    sizes += [int(x) for x in 10 ** rng.uniform(0, 9, 300)]
+    for capacity, slots in ((3072, 148), (1536, 296), (3072, 132), (1536, 7)):
+        for n in sizes:
+            cpt = lib.pvv_iv_tile_plan(n, capacity, slots)
+            assert 32 <= cpt <= capacity and cpt % 32 == 0, (n, capacity, slots, cpt)
+            grid = -(-n // cpt)
+            waves_min = -(-n // (slots * capacity))
+            assert grid * cpt >= n
+            assert -(-grid // slots) == waves_min, (n, capacity, slots, cpt, grid)      # never an extra wave
+            even = -(-n // (waves_min * slots))
+            assert cpt < even + 32 or cpt == capacity, (n, capacity, slots, cpt, even)  # as even as the alignment allows
+    # full tiles once the column is long: the plan converges to the capacity
+    assert lib.pvv_iv_tile_plan(148 * 3072 * 50, 3072, 148) == 3072
+    for bad in ((0, 3072, 148), (10, 100, 148), (10, 3072, 0)):
+        assert lib.pvv_iv_tile_plan(*bad) < 0
